@@ -1,0 +1,161 @@
+"""ctypes bindings for the CPU checkers under oracle/ (TEST INFRASTRUCTURE ONLY).
+
+* ``port``  -> oracle/liboracle.so          plain-C restatement (oracle/gebp_port.c, hp_ref.c, blat3_port.c)
+* ``ref``   -> oracle/_ref/*.so             the unmodified reference compiled by oracle/Makefile (may be absent)
+
+The product package ``eigen_b200`` never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+TYPES = {"s": 0, "d": 1, "c": 2, "z": 3}
+NP_DTYPE = {"s": np.float32, "d": np.float64, "c": np.complex64, "z": np.complex128}
+EPS = {"s": 2.0 ** -23, "d": 2.0 ** -52, "c": 2.0 ** -23, "z": 2.0 ** -52}
+
+_i = C.c_int
+_ip = C.POINTER(C.c_int)
+_vp = C.c_void_p
+_cp = C.c_char_p
+
+GEMM_ARGTYPES = [_cp, _cp, _ip, _ip, _ip, _vp, _vp, _ip, _vp, _ip, _vp, _vp, _ip]
+
+
+class Blat3Report(C.Structure):
+    _fields_ = [("ncalls", C.c_int), ("errmax", C.c_double), ("fatal", C.c_int), ("bad_param", C.c_int),
+                ("msg", C.c_char * 200)]
+
+
+def _build_port():
+    so = os.path.join(ORACLE_DIR, "liboracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gebp_port.c", "gebp_impl.h", "hp_ref.c", "blat3_port.c", "oracle.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "port"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_port = None
+_ref_blas = None
+_ref_shim = None
+
+
+def port():
+    """liboracle.so, loaded RTLD_GLOBAL so that its xerbla_ (the xBLAT3 tester's) interposes the weak ones."""
+    global _port
+    if _port is None:
+        lib = C.CDLL(_build_port(), mode=C.RTLD_GLOBAL)
+        for sfx in "sdcz":
+            f = getattr(lib, "oracle_%sgemm_" % sfx)
+            f.argtypes = GEMM_ARGTYPES
+            f.restype = _i
+        lib.oracle_gemm_omp.argtypes = [_i, C.c_char, C.c_char, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i]
+        lib.oracle_hp_gemm.argtypes = [_i, C.c_char, C.c_char, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp]
+        lib.oracle_hp_gemm.restype = None
+        lib.oracle_blat3_chk1.argtypes = [_i, _vp, C.POINTER(Blat3Report)]
+        lib.oracle_blat3_chk1.restype = None
+        lib.oracle_blat3_chke.argtypes = [_i, _vp, _vp, C.c_char_p, _i]
+        lib.oracle_blat3_chke.restype = _i
+        lib.oracle_set_cache_sizes.argtypes = [C.c_long] * 3
+        lib.oracle_blocking_sizes.argtypes = [_i, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long), _i]
+        lib.oracle_gebp_traits.argtypes = [_i, _ip, _ip, _ip]
+        lib.oracle_pack_lhs.argtypes = [_i, _vp, _vp, C.c_long, C.c_long, C.c_long, _i, _i]
+        lib.oracle_pack_rhs.argtypes = [_i, _vp, _vp, C.c_long, C.c_long, C.c_long, _i, _i]
+        lib.oracle_parallel_partition.argtypes = [_i, C.c_long, C.c_long, C.c_long, _i, _i] + [C.POINTER(C.c_long)] * 4
+        lib.oracle_parallel_partition.restype = _i
+        lib.oracle_blat3_dbeg.restype = C.c_double
+        _port = lib
+    return _port
+
+
+def have_ref():
+    d = os.path.join(ORACLE_DIR, "_ref")
+    return os.path.exists(os.path.join(d, "libeigen_blas_ref.so")) and os.path.exists(os.path.join(d, "libeigen_gebp_omp.so"))
+
+
+def ref_blas():
+    """The reference's own blas/ library (sgemm_/dgemm_/cgemm_/zgemm_ ... of blas/level3_impl.h)."""
+    global _ref_blas
+    if _ref_blas is None:
+        port()  # tester xerbla_ first
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libeigen_blas_ref.so"), mode=C.RTLD_LOCAL)
+        for sfx in "sdcz":
+            f = getattr(lib, "%sgemm_" % sfx)
+            f.argtypes = GEMM_ARGTYPES
+            f.restype = _i
+        _ref_blas = lib
+    return _ref_blas
+
+
+def ref_shim():
+    """Eigen's expression API + OpenMP gebp path (oracle/ref_eigen_shim.cpp compiled against the reference)."""
+    global _ref_shim
+    if _ref_shim is None:
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libeigen_gebp_omp.so"), mode=C.RTLD_LOCAL)
+        for sfx in "sdcz":
+            f = getattr(lib, "ref_eigen_gemm_%s" % sfx)
+            f.argtypes = [C.c_char, C.c_char, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i]
+            f.restype = None
+        lib.ref_cache_sizes.argtypes = [C.POINTER(C.c_long)] * 3
+        lib.ref_blocking_sizes.argtypes = [_i, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long), _i]
+        lib.ref_gebp_traits.argtypes = [_i, _ip, _ip, _ip]
+        for n in ("ref_pack_lhs_d", "ref_pack_rhs_d", "ref_pack_lhs_s", "ref_pack_rhs_s"):
+            getattr(lib, n).argtypes = [_vp, _vp, C.c_long, C.c_long, C.c_long, _i]
+        for n in ("ref_pack_lhs_z", "ref_pack_rhs_z"):
+            getattr(lib, n).argtypes = [_vp, _vp, C.c_long, C.c_long, C.c_long, _i, _i]
+        _ref_shim = lib
+    return _ref_shim
+
+
+def sync_cache_sizes():
+    """Give the port the cache sizes the reference detected on this host, so kc/mc/nc (and rounding) coincide."""
+    l1, l2, l3 = C.c_long(), C.c_long(), C.c_long()
+    ref_shim().ref_cache_sizes(C.byref(l1), C.byref(l2), C.byref(l3))
+    port().oracle_set_cache_sizes(l1.value, l2.value, l3.value)
+    return l1.value, l2.value, l3.value
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+def call_gemm(fn, t, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc):
+    """Call an F77-ABI gemm: everything by pointer.  a/b/c are 1-D or F-ordered numpy arrays of the right dtype."""
+    dt = NP_DTYPE[t]
+    al = np.array([alpha], dtype=dt)
+    be = np.array([beta], dtype=dt)
+    ints = [C.c_int(v) for v in (m, n, k, lda, ldb, ldc)]
+    return fn(ta.encode(), tb.encode(), C.byref(ints[0]), C.byref(ints[1]), C.byref(ints[2]), _ptr(al), _ptr(a),
+              C.byref(ints[3]), _ptr(b), C.byref(ints[4]), _ptr(be), _ptr(c), C.byref(ints[5]))
+
+
+def hp_gemm(t, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc, rows=None):
+    """Long-double reference.  Returns (C_ref, G) for the selected rows; C_ref is float64/complex128."""
+    dt = NP_DTYPE[t]
+    al = np.array([alpha], dtype=dt)
+    be = np.array([beta], dtype=dt)
+    cplx = t in "cz"
+    if rows is None:
+        ridx, nr = None, m
+    else:
+        ridx = np.ascontiguousarray(rows, dtype=np.int32)
+        nr = len(ridx)
+    out = np.zeros((nr, n), dtype=np.complex128 if cplx else np.float64, order="F")
+    g = np.zeros((nr, n), dtype=np.float64, order="F")
+    port().oracle_hp_gemm(TYPES[t], ta.encode(), tb.encode(), m, n, k, _ptr(al), _ptr(a), lda, _ptr(b), ldb, _ptr(be),
+                          _ptr(c), ldc, _ptr(ridx), nr, _ptr(out), _ptr(g))
+    return out, g
+
+
+def rand_matrix(rng, t, rows, cols, ld=None):
+    """Uniform [-1,1] like Eigen's setRandom (MathFunctions.h:628-637); returns an (ld x cols) F-ordered array."""
+    ld = rows if ld is None else ld
+    dt = NP_DTYPE[t]
+    x = rng.uniform(-1, 1, size=(max(ld, 1), cols))
+    if t in "cz":
+        x = x + 1j * rng.uniform(-1, 1, size=(max(ld, 1), cols))
+    return np.asfortranarray(x.astype(dt))
