@@ -1,0 +1,60 @@
+// eigen_b200/csrc/common.cuh -- shared declarations of libb200blas (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200 {
+
+enum Op : int { OP_N = 0, OP_T = 1, OP_C = 2, OP_INVALID = 0xff };  // blas/common.h:24-42
+enum Type : int { TY_S = 0, TY_D = 1, TY_C = 2, TY_Z = 3 };
+
+// One product C = alpha*op(A)*op(B) + beta*C on device memory; leading dimensions in elements of the scalar type.
+struct GemmProblem {
+  int type;
+  int opa, opb;
+  int64_t m, n, k;
+  double alpha[2], beta[2];  // widened on the host; kernels narrow to their scalar type
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* C; int64_t ldc;
+};
+
+static inline int type_bytes(int t) { return t == TY_S ? 4 : t == TY_Z ? 16 : 8; }
+
+// kernel launchers (one translation unit each); return cudaError_t as int, bump the launch counter themselves
+int launch_simt(const GemmProblem& p, cudaStream_t s);
+int launch_dmma(const GemmProblem& p, cudaStream_t s);      // type D / Z
+int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t workspace_bytes);  // type S / C
+size_t tf32x3_workspace_bytes(const GemmProblem& p);
+bool dmma_supported(const GemmProblem& p);
+bool tf32x3_supported(const GemmProblem& p);
+int launch_scale_c(const GemmProblem& p, cudaStream_t s);   // C = beta*C only (k == 0)
+double pipe_peak(int pipe, int millis);
+
+void count_launch(int n = 1);
+void note_variant(const char* name);
+
+#define B200_CUDA_TRY(expr)                                  \
+  do {                                                       \
+    cudaError_t _e = (expr);                                 \
+    if (_e != cudaSuccess) return (int)_e;                   \
+  } while (0)
+
+// ---- device helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// cp.async with zero fill: copies src_bytes (<= BYTES) and zero-fills the rest of the BYTES-wide destination
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gmem_src, int src_bytes) {
+  static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+}  // namespace b200

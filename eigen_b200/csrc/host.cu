@@ -1,0 +1,346 @@
+// eigen_b200/csrc/host.cu -- the C-ABI host layer of libb200blas.so.
+//
+// Mirrors the reference's BLAS seam for the dense product:
+//   EIGEN_BLAS_FUNC(gemm)            blas/level3_impl.h:12-76   (argument checks, info codes, quick returns, beta)
+//   OP()                             blas/common.h:39-42        (case-insensitive N/T/C)
+//   xerbla_                          blas/xerbla.cpp:15-19      (weak, overridable)
+//   parallelize_gemm under EIGEN_USE_BLAS is a single call (Parallelizer.h:88-97): one ?gemm_ per product.
+// Host operands are staged through CUDA streams: A is uploaded once, B and C travel in column slabs so that the
+// upload of slab j+1, the product on slab j and the download of slab j-1 overlap (the GPU analogue of the kc/nc
+// panel streaming of GeneralMatrixMatrix.h:155-198).  There is no CPU fallback.
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "../../include/b200blas.h"
+#include "common.cuh"
+
+namespace b200 {
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_forced_variant{-1};
+static thread_local char t_variant[64] = "";
+static thread_local char t_error[256] = "";
+static thread_local uint64_t t_h2d = 0, t_d2h = 0;
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void note_variant(const char* name) {
+  strncpy(t_variant, name, sizeof(t_variant) - 1);
+  t_variant[sizeof(t_variant) - 1] = 0;
+}
+static int fail(int cuda_err) {
+  if (cuda_err != 0) {
+    snprintf(t_error, sizeof t_error, "%s", cudaGetErrorString((cudaError_t)cuda_err));
+    cudaGetLastError();  // clear sticky-less errors
+  }
+  return cuda_err;
+}
+
+static int op_of(char x) {
+  return (x == 'N' || x == 'n') ? OP_N : (x == 'T' || x == 't') ? OP_T : (x == 'C' || x == 'c') ? OP_C : OP_INVALID;
+}
+
+static int forced_variant() {
+  int v = g_forced_variant.load();
+  if (v >= 0) return v;
+  static int env_v = [] {
+    const char* e = getenv("B200BLAS_VARIANT");
+    if (!e) return (int)B200BLAS_AUTO;
+    if (!strcmp(e, "simt")) return (int)B200BLAS_SIMT;
+    if (!strcmp(e, "dmma")) return (int)B200BLAS_DMMA;
+    if (!strcmp(e, "tf32x3")) return (int)B200BLAS_TF32X3;
+    return (int)B200BLAS_AUTO;
+  }();
+  return env_v;
+}
+
+// Variant choice.  Tensor tiles are 128x128 (DMMA) / 128x256 (tcgen05); below about one tile of work, or when the
+// operands cannot be fed to the tensor variant, the SIMT kernel wins (thresholds: profiles/variant_sweep_r01.md).
+static int choose_variant(const GemmProblem& p, int requested) {
+  int v = requested != B200BLAS_AUTO ? requested : forced_variant();
+  const bool dz = (p.type == TY_D || p.type == TY_Z);
+  if (v == B200BLAS_DMMA && !(dz && dmma_supported(p))) v = B200BLAS_AUTO;
+  if (v == B200BLAS_TF32X3 && !(!dz && tf32x3_supported(p))) v = B200BLAS_AUTO;
+  if (v != B200BLAS_AUTO) return v;
+  if (p.k == 0) return B200BLAS_SIMT;
+  const double work = (double)p.m * (double)p.n * (double)p.k;
+  if (dz) {
+    if (dmma_supported(p) && p.m * p.n >= 64 * 64 && p.k >= 8 && work >= 64.0 * 64.0 * 64.0) return B200BLAS_DMMA;
+    return B200BLAS_SIMT;
+  }
+  if (tf32x3_supported(p) && p.m >= 128 && p.n >= 128 && p.k >= 32 && work >= 256.0 * 256.0 * 256.0)
+    return B200BLAS_TF32X3;
+  return B200BLAS_SIMT;
+}
+
+static int run_device(const GemmProblem& p, cudaStream_t s, int variant) {
+  const int v = choose_variant(p, variant);
+  if (v == B200BLAS_DMMA) return fail(launch_dmma(p, s));
+  if (v == B200BLAS_TF32X3) {
+    const size_t ws = tf32x3_workspace_bytes(p);
+    void* w = nullptr;
+    if (ws) { const int e = (int)cudaMallocAsync(&w, ws, s); if (e) return fail(e); }
+    const int e = launch_tf32x3(p, s, w, ws);
+    if (w) cudaFreeAsync(w, s);
+    return fail(e);
+  }
+  return fail(launch_simt(p, s));
+}
+
+// ---- argument checks of blas/level3_impl.h:47-57 ---------------------------------------------------------
+static int check_args(int opa, int opb, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc) {
+  if (opa == OP_INVALID) return 1;
+  if (opb == OP_INVALID) return 2;
+  if (m < 0) return 3;
+  if (n < 0) return 4;
+  if (k < 0) return 5;
+  if (lda < std::max<int64_t>(1, opa == OP_N ? m : k)) return 8;
+  if (ldb < std::max<int64_t>(1, opb == OP_N ? k : n)) return 10;
+  if (ldc < std::max<int64_t>(1, m)) return 13;
+  return 0;
+}
+static const char* k_names[4] = {"SGEMM ", "DGEMM ", "CGEMM ", "ZGEMM "};
+
+static void load_scalar(int type, const void* p, double out[2]) {
+  switch (type) {
+    case TY_S: out[0] = *(const float*)p; out[1] = 0; break;
+    case TY_D: out[0] = *(const double*)p; out[1] = 0; break;
+    case TY_C: out[0] = ((const float*)p)[0]; out[1] = ((const float*)p)[1]; break;
+    default: out[0] = ((const double*)p)[0]; out[1] = ((const double*)p)[1]; break;
+  }
+}
+
+// ---- per-process staging context ---------------------------------------------------------------------------
+struct Staging {
+  std::mutex mu;
+  int dev = -1;
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  void* dbuf[3] = {nullptr, nullptr, nullptr};
+  size_t dcap[3] = {0, 0, 0};
+  static constexpr int MAX_SLABS = 64;
+  cudaEvent_t ev_in[MAX_SLABS], ev_comp[MAX_SLABS], ev_a = nullptr;
+  bool ready = false;
+
+  int init() {
+    int d = 0;
+    B200_CUDA_TRY(cudaGetDevice(&d));
+    if (ready && d == dev) return 0;
+    release();
+    dev = d;
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_SLABS; ++i) {
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+    }
+    ready = true;
+    return 0;
+  }
+  int reserve(int i, size_t bytes) {
+    if (bytes <= dcap[i]) return 0;
+    if (dbuf[i]) { cudaFree(dbuf[i]); dbuf[i] = nullptr; dcap[i] = 0; }
+    B200_CUDA_TRY(cudaMalloc(&dbuf[i], bytes));
+    dcap[i] = bytes;
+    return 0;
+  }
+  void release() {
+    if (!ready) return;
+    for (int i = 0; i < 3; ++i) { if (dbuf[i]) cudaFree(dbuf[i]); dbuf[i] = nullptr; dcap[i] = 0; }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_comp) cudaStreamDestroy(s_comp);
+    if (s_out) cudaStreamDestroy(s_out);
+    if (ev_a) cudaEventDestroy(ev_a);
+    for (int i = 0; i < MAX_SLABS; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); }
+    s_in = s_comp = s_out = nullptr; ev_a = nullptr;
+    ready = false;
+  }
+};
+static Staging g_stage;
+
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+static int64_t round_up(int64_t x, int64_t q) { return (x + q - 1) / q * q; }
+
+// Host-operand product: stage, multiply, return.  Returns a cudaError_t (0 = ok).
+static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k, const double alpha[2], const void* a,
+                    int64_t lda, const void* b, int64_t ldb, const double beta[2], void* c, int64_t ldc) {
+  std::lock_guard<std::mutex> lock(g_stage.mu);
+  Staging& st = g_stage;
+  { const int e = st.init(); if (e) return e; }
+  const size_t es = (size_t)type_bytes(type);
+  const bool beta_zero = (beta[0] == 0.0 && beta[1] == 0.0);
+  const bool have_product = k > 0;
+  // device images: column-major, leading dimension = rows rounded up to 16 bytes * 2 (keeps every column 16-byte aligned)
+  const int64_t ra = (opa == OP_N) ? m : k, ca = (opa == OP_N) ? k : m;
+  const int64_t rb = (opb == OP_N) ? k : n, cb = (opb == OP_N) ? n : k;
+  const int64_t q = 32 / (int64_t)es > 0 ? 32 / (int64_t)es : 1;
+  const int64_t dlda = round_up(std::max<int64_t>(ra, 1), q), dldb = round_up(std::max<int64_t>(rb, 1), q),
+                dldc = round_up(m, q);
+  if (have_product) {
+    { const int e = st.reserve(0, (size_t)dlda * (size_t)std::max<int64_t>(ca, 1) * es); if (e) return e; }
+    { const int e = st.reserve(1, (size_t)dldb * (size_t)std::max<int64_t>(cb, 1) * es); if (e) return e; }
+  }
+  { const int e = st.reserve(2, (size_t)dldc * (size_t)n * es); if (e) return e; }
+  char* dA = (char*)st.dbuf[0];
+  char* dB = (char*)st.dbuf[1];
+  char* dC = (char*)st.dbuf[2];
+  t_h2d = t_d2h = 0;
+
+  // column slabs of C (and of op(B)): ~16 slabs, at least 512 columns wide, multiples of 256 columns
+  const double total_bytes = (double)es * ((double)m * k + (double)k * n + 2.0 * m * n);
+  int64_t slab = n;
+  if (total_bytes > 32e6 && n >= 1024) slab = std::max<int64_t>(512, round_up((n + 15) / 16, 256));
+  int nslabs = (int)((n + slab - 1) / slab);
+  if (nslabs > Staging::MAX_SLABS) { slab = round_up((n + Staging::MAX_SLABS - 1) / Staging::MAX_SLABS, 256); nslabs = (int)((n + slab - 1) / slab); }
+
+  if (have_product) {
+    B200_CUDA_TRY(cudaMemcpy2DAsync(dA, (size_t)dlda * es, a, (size_t)lda * es, (size_t)ra * es, (size_t)ca,
+                                    cudaMemcpyHostToDevice, st.s_in));
+    t_h2d += (uint64_t)ra * ca * es;
+    B200_CUDA_TRY(cudaEventRecord(st.ev_a, st.s_in));
+    B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_a, 0));
+  }
+  for (int j = 0; j < nslabs; ++j) {
+    const int64_t j0 = (int64_t)j * slab, nj = std::min<int64_t>(slab, n - j0);
+    if (have_product) {
+      if (opb == OP_N) {
+        B200_CUDA_TRY(cudaMemcpy2DAsync(dB + (size_t)j0 * dldb * es, (size_t)dldb * es, (const char*)b + (size_t)j0 * ldb * es,
+                                        (size_t)ldb * es, (size_t)k * es, (size_t)nj, cudaMemcpyHostToDevice, st.s_in));
+      } else {
+        B200_CUDA_TRY(cudaMemcpy2DAsync(dB + (size_t)j0 * es, (size_t)dldb * es, (const char*)b + (size_t)j0 * es,
+                                        (size_t)ldb * es, (size_t)nj * es, (size_t)k, cudaMemcpyHostToDevice, st.s_in));
+      }
+      t_h2d += (uint64_t)k * nj * es;
+    }
+    if (!beta_zero) {  // beta == 0: C is never read, so it is not uploaded either (blas/level3_impl.h:64)
+      B200_CUDA_TRY(cudaMemcpy2DAsync(dC + (size_t)j0 * dldc * es, (size_t)dldc * es, (const char*)c + (size_t)j0 * ldc * es,
+                                      (size_t)ldc * es, (size_t)m * es, (size_t)nj, cudaMemcpyHostToDevice, st.s_in));
+      t_h2d += (uint64_t)m * nj * es;
+    }
+    B200_CUDA_TRY(cudaEventRecord(st.ev_in[j], st.s_in));
+    B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_in[j], 0));
+    GemmProblem p;
+    p.type = type; p.opa = opa; p.opb = opb; p.m = m; p.n = nj; p.k = k;
+    p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = beta[0]; p.beta[1] = beta[1];
+    p.A = dA; p.lda = dlda;
+    p.B = (opb == OP_N) ? dB + (size_t)j0 * dldb * es : dB + (size_t)j0 * es; p.ldb = dldb;
+    p.C = dC + (size_t)j0 * dldc * es; p.ldc = dldc;
+    { const int e = run_device(p, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
+    B200_CUDA_TRY(cudaEventRecord(st.ev_comp[j], st.s_comp));
+    B200_CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_comp[j], 0));
+    // only the m x nj window travels back: rows m..ldc-1 of the caller's C stay untouched
+    B200_CUDA_TRY(cudaMemcpy2DAsync((char*)c + (size_t)j0 * ldc * es, (size_t)ldc * es, dC + (size_t)j0 * dldc * es,
+                                    (size_t)dldc * es, (size_t)m * es, (size_t)nj, cudaMemcpyDeviceToHost, st.s_out));
+    t_d2h += (uint64_t)m * nj * es;
+  }
+  B200_CUDA_TRY(cudaStreamSynchronize(st.s_out));
+  B200_CUDA_TRY(cudaStreamSynchronize(st.s_comp));
+  B200_CUDA_TRY(cudaStreamSynchronize(st.s_in));
+  return 0;
+}
+
+static int gemm_entry(int type, const char* ta, const char* tb, const int* pm, const int* pn, const int* pk,
+                      const void* palpha, const void* a, const int* plda, const void* b, const int* pldb,
+                      const void* pbeta, void* c, const int* pldc) {
+  const int opa = op_of(*ta), opb = op_of(*tb);
+  int info = check_args(opa, opb, *pm, *pn, *pk, *plda, *pldb, *pldc);
+  if (info) return xerbla_(k_names[type], &info, 6);
+  if (*pm == 0 || *pn == 0) return 0;
+  double alpha[2], beta[2];
+  load_scalar(type, palpha, alpha);
+  load_scalar(type, pbeta, beta);
+  t_error[0] = 0;
+  int err;
+  if (is_device_ptr(c)) {
+    GemmProblem p;
+    p.type = type; p.opa = opa; p.opb = opb; p.m = *pm; p.n = *pn; p.k = *pk;
+    p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = beta[0]; p.beta[1] = beta[1];
+    p.A = a; p.lda = *plda; p.B = b; p.ldb = *pldb; p.C = c; p.ldc = *pldc;
+    err = run_device(p, nullptr, B200BLAS_AUTO);
+    if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
+  } else {
+    err = fail(run_host(type, opa, opb, *pm, *pn, *pk, alpha, a, *plda, b, *pldb, beta, c, *pldc));
+  }
+  if (err) {
+    // no CPU fallback by contract: CUDA failures surface through xerbla_ with the reserved info -1
+    info = -1;
+    return xerbla_(k_names[type], &info, 6);
+  }
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+__attribute__((weak)) int xerbla_(const char* name, int* info, int) {
+  printf("Eigen BLAS ERROR #%i: %s\n", *info, name);
+  return 0;
+}
+
+int sgemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const float* alpha, const float* a,
+           const int* lda, const float* b, const int* ldb, const float* beta, float* c, const int* ldc) {
+  return gemm_entry(TY_S, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+int dgemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const double* alpha,
+           const double* a, const int* lda, const double* b, const int* ldb, const double* beta, double* c,
+           const int* ldc) {
+  return gemm_entry(TY_D, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+int cgemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const float* alpha, const float* a,
+           const int* lda, const float* b, const int* ldb, const float* beta, float* c, const int* ldc) {
+  return gemm_entry(TY_C, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+int zgemm_(const char* ta, const char* tb, const int* m, const int* n, const int* k, const double* alpha,
+           const double* a, const int* lda, const double* b, const int* ldb, const double* beta, double* c,
+           const int* ldc) {
+  return gemm_entry(TY_Z, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
+}
+
+int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, const void* alpha, const void* dA,
+                      int64_t lda, const void* dB, int64_t ldb, const void* beta, void* dC, int64_t ldc, void* stream,
+                      int variant) {
+  if (type < 0 || type > 3) return -1;
+  const int opa = op_of(transa), opb = op_of(transb);
+  int info = check_args(opa, opb, m, n, k, lda, ldb, ldc);
+  if (info) return xerbla_(k_names[type], &info, 6);
+  if (m == 0 || n == 0) return 0;
+  GemmProblem p;
+  p.type = type; p.opa = opa; p.opb = opb; p.m = m; p.n = n; p.k = k;
+  load_scalar(type, alpha, p.alpha);
+  load_scalar(type, beta, p.beta);
+  p.A = dA; p.lda = lda; p.B = dB; p.ldb = ldb; p.C = dC; p.ldc = ldc;
+  t_error[0] = 0;
+  const int err = run_device(p, (cudaStream_t)stream, variant);
+  if (err) { info = -1; return xerbla_(k_names[type], &info, 6); }
+  return 0;
+}
+
+int b200blas_version(void) { return 100; }
+int b200blas_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return major == 10;
+}
+const char* b200blas_last_error(void) { return t_error; }
+const char* b200blas_last_variant(void) { return t_variant; }
+uint64_t b200blas_kernel_launches(void) { return g_launches.load(); }
+void b200blas_set_variant(int variant) { g_forced_variant.store(variant == B200BLAS_AUTO ? -1 : variant); }
+void b200blas_last_transfer(uint64_t* h2d, uint64_t* d2h) { if (h2d) *h2d = t_h2d; if (d2h) *d2h = t_d2h; }
+void b200blas_release(void) { std::lock_guard<std::mutex> lock(g_stage.mu); g_stage.release(); }
+double b200blas_pipe_peak(int pipe, int millis) { return pipe_peak(pipe, millis); }
+
+}  // extern "C"

@@ -1,0 +1,191 @@
+"""Parity of the sm_100a library against the CPU oracle, through the C ABI (run with -m gpu on a B200).
+
+Bar (BASELINE.json north_star): relative Frobenius error <= c*k*eps of the scalar type against the long-double
+reference, here with c = 1 (TOL_FRO), plus the netlib component-wise gauge ratio |c-c_ref|/(eps*G) < 16 that the
+reference's own blas/testing harness applies (dblat3.f:2587-2596).  The oracle port's (= Eigen gebp's) own error
+against the same reference is computed next to ours and we must stay within 4x of it or under 2*sqrt(k)*eps.
+"""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import eigen_b200
+import oracle_api as oa
+
+pytestmark = pytest.mark.gpu
+P = oa.port()
+HERE = os.path.dirname(os.path.abspath(__file__))
+TOL_FRO = 1.0     # * k * eps
+TOL_RATIO = 16.0  # xBLAT3 THRESH, blas/testing/dblat3.dat:8
+
+
+@pytest.fixture(scope="module")
+def L():
+    lib = eigen_b200.require_device()
+    yield lib
+    lib.b200blas_set_variant(0)
+
+
+def _variants(t):
+    return ["simt", "dmma"] if t in "dz" else ["simt", "tf32x3"]
+
+
+def _check(t, ta, tb, m, n, k, al, be, A, B, C0, c, ldc, rows=None, port_too=True):
+    ref, g = oa.hp_gemm(t, ta, tb, m, n, k, al, A, A.shape[0], B, B.shape[0], be, C0, ldc, rows=rows)
+    got = c[:m] if rows is None else c[rows]
+    eps = oa.EPS[t]
+    ratio = (np.abs(got - ref) / (eps * np.maximum(g, 1e-300))).max() if m and n else 0.0
+    fro = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-300)
+    assert ratio < TOL_RATIO, (t, ta, tb, m, n, k, "gauge ratio", ratio, eigen_b200.last_variant())
+    assert fro <= TOL_FRO * max(k, 1) * eps, (t, ta, tb, m, n, k, "fro", fro)
+    if port_too and rows is None and m * n * k <= 4e8:
+        c2 = C0.copy(order="F")
+        oa.call_gemm(getattr(P, "oracle_%sgemm_" % t), t, ta, tb, m, n, k, al, A, A.shape[0], B, B.shape[0], be, c2, ldc)
+        fro_port = np.linalg.norm(c2[:m] - ref) / max(np.linalg.norm(ref), 1e-300)
+        assert fro <= max(4.0 * fro_port, 2.0 * np.sqrt(max(k, 1)) * eps), (t, m, n, k, fro, fro_port)
+    return fro, ratio
+
+
+@pytest.mark.parametrize("t", list("sdcz"))
+def test_xblat3_sweep_and_error_exits(L, t):
+    """The reference's own acceptance test for ?gemm_ (blas/testing/*blat3.f), restated in oracle/blat3_port.c,
+    run against the F77 entry points with host arrays: 17496 calls, ld = dim+1, N/T/C, alpha/beta grids, argument
+    preservation incl. the padding rows of C, then the 28 error exits."""
+    for v in _variants(t):
+        L.b200blas_set_variant(eigen_b200.VARIANT[v])
+        rep = oa.Blat3Report()
+        P.oracle_blat3_chk1(oa.TYPES[t], C.cast(getattr(L, t + "gemm_"), C.c_void_p), C.byref(rep))
+        assert rep.ncalls == 17496
+        assert not rep.fatal, (v, rep.msg)
+        assert rep.errmax < 16.0, (v, rep.errmax)
+    L.b200blas_set_variant(0)
+    log = C.create_string_buffer(4096)
+    assert P.oracle_blat3_chke(oa.TYPES[t], C.cast(getattr(L, t + "gemm_"), C.c_void_p), None, log, 4096) == 0, log.value
+
+
+SHAPES = [(1, 1, 1), (5, 3, 2), (17, 9, 33), (64, 64, 64), (65, 63, 67), (128, 128, 128), (129, 257, 40),
+          (200, 180, 700), (515, 130, 401), (96, 7, 1000), (7, 300, 129), (256, 512, 1024), (1000, 1, 1000),
+          (1, 1000, 1000), (333, 444, 5)]
+
+
+@pytest.mark.parametrize("t", list("sdcz"))
+def test_random_shapes_all_ops_vs_oracle(L, t):
+    """Seeded uniform[-1,1] inputs like bench/bench_gemm.cpp:211-214; every op pair, ragged sizes, ld > dim,
+    the xBLAT alpha/beta values; each kernel variant forced in turn, then the automatic choice."""
+    rng = np.random.default_rng(1234)
+    cplx = t in "cz"
+    alphas = [1.0, (0.7 - 0.9j) if cplx else 0.7, -1.0]
+    betas = [1.0, (1.3 - 1.1j) if cplx else 1.3, 0.0]
+    worst = 0.0
+    for v in _variants(t) + ["auto"]:
+        L.b200blas_set_variant(eigen_b200.VARIANT[v])
+        for si, (m, n, k) in enumerate(SHAPES):
+            for oi, (ta, tb) in enumerate([(x, y) for x in "NTC" for y in "NTC"]):
+                if (si + oi) % 3 and m * n * k > 1e6:
+                    continue  # large shapes: a third of the op pairs per shape, rotating
+                ra, ca = (m, k) if ta == "N" else (k, m)
+                rb, cb = (k, n) if tb == "N" else (n, k)
+                A = oa.rand_matrix(rng, t, ra, ca, ld=ra + (si % 3))
+                B = oa.rand_matrix(rng, t, rb, cb, ld=rb + ((si + 1) % 3))
+                ldc = m + (si % 2) * 3
+                C0 = oa.rand_matrix(rng, t, m, n, ld=ldc)
+                if betas[(si + oi) % 3] == 0.0:
+                    C0[:m] = np.nan  # beta == 0 must not read C (blas/level3_impl.h:64)
+                c = C0.copy(order="F")
+                al, be = alphas[(si + oi) % 3], betas[(si + oi) % 3]
+                r = oa.call_gemm(getattr(L, t + "gemm_"), t, ta, tb, m, n, k, al, A, A.shape[0], B, B.shape[0], be, c, ldc)
+                assert r == 0, eigen_b200.last_error()
+                assert c[m:].tobytes() == C0[m:].tobytes(), "padding rows of C were touched"
+                Cin = C0 if be != 0.0 else np.zeros_like(C0)
+                fro, ratio = _check(t, ta, tb, m, n, k, al, be, A, B, Cin, c, ldc)
+                worst = max(worst, ratio)
+    L.b200blas_set_variant(0)
+    print("worst gauge ratio", t, worst)
+
+
+@pytest.mark.parametrize("t", list("sdcz"))
+def test_quick_returns_and_k0(L, t):
+    rng = np.random.default_rng(2)
+    A = oa.rand_matrix(rng, t, 8, 8)
+    C0 = oa.rand_matrix(rng, t, 8, 8)
+    c = C0.copy(order="F")
+    # k == 0: only the beta scaling (blas/level3_impl.h:62-69), alpha = NaN must not leak
+    oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "N", 8, 8, 0, np.nan, A, 8, A, 8, 1.3, c, 8)
+    assert np.allclose(c, C0 * oa.NP_DTYPE[t](1.3), rtol=4 * oa.EPS[t])
+    c = C0.copy(order="F")
+    oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "N", 8, 8, 0, 1.0, A, 8, A, 8, 0.0, c, 8)
+    assert np.all(c == 0)
+    # zero-sized products leave everything alone (test/product_extra.cpp:123-147)
+    c = C0.copy(order="F")
+    oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "N", 0, 8, 8, 1.0, A, 8, A, 8, 0.0, c, 8)
+    assert c.tobytes() == C0.tobytes()
+
+
+@pytest.mark.parametrize("t", list("sdcz"))
+def test_ones_known_answer(L, t):
+    """test/product_extra.cpp:313-354 (Ones*Ones == k) through every op pair."""
+    dt = oa.NP_DTYPE[t]
+    for kk in (4, 300):
+        a = np.ones((kk, kk), dtype=dt, order="F")
+        for ta in "NTC":
+            for tb in "NTC":
+                c = np.zeros((kk, kk), dtype=dt, order="F")
+                oa.call_gemm(getattr(L, t + "gemm_"), t, ta, tb, kk, kk, kk, 1.0, a, kk, a, kk, 0.0, c, kk)
+                assert np.all(c == kk)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))))
+def test_committed_reference_outputs(L, path):
+    """Outputs of the reference library itself (tests/golden, made by make_golden.py): ours must agree with them
+    to the gauge ratio both sides are entitled to (2 x 16 eps G is the loosest the netlib criterion allows; we
+    require 8)."""
+    z = np.load(path)
+    t = str(z["t"])
+    m, n, k = [int(v) for v in z["mnk"]]
+    ta, tb = str(z["ta"]), str(z["tb"])
+    A, B, C0, Cref = [np.asfortranarray(z[x]) for x in ("A", "B", "C0", "Cref")]
+    al, be = z["alpha"].item(), z["beta"].item()
+    c = C0.copy(order="F")
+    assert oa.call_gemm(getattr(L, t + "gemm_"), t, ta, tb, m, n, k, al, A, A.shape[0], B, B.shape[0], be, c, c.shape[0]) == 0
+    assert c[m:].tobytes() == Cref[m:].tobytes()
+    _, g = oa.hp_gemm(t, ta, tb, m, n, k, al, A, A.shape[0], B, B.shape[0], be, C0, C0.shape[0])
+    assert (np.abs(c[:m] - Cref[:m]) / (oa.EPS[t] * g)).max() < 8.0
+
+
+def test_device_pointer_api_and_streams(L):
+    """Section 2 of include/b200blas.h: device-resident operands (torch tensors), asynchronous on a stream."""
+    import torch
+    torch.manual_seed(0)
+    for t, dt in (("d", torch.float64), ("s", torch.float32), ("z", torch.complex128), ("c", torch.complex64)):
+        m, n, k = 300, 260, 190
+        A = (torch.rand(k, m, dtype=dt, device="cuda") * 2 - 1)  # column-major m x k == row-major k x m
+        B = (torch.rand(n, k, dtype=dt, device="cuda") * 2 - 1)
+        Cd = torch.ones(n, m, dtype=dt, device="cuda")
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            r = eigen_b200.gemm_dev(t, "N", "N", m, n, k, 1.0, A, m, B, k, 1.0, Cd, m)
+        s.synchronize()
+        assert r == 0
+        An = np.asfortranarray(A.cpu().numpy().T)
+        Bn = np.asfortranarray(B.cpu().numpy().T)
+        C0 = np.ones((m, n), dtype=oa.NP_DTYPE[t], order="F")
+        c = np.asfortranarray(Cd.cpu().numpy().T)
+        _check(t, "N", "N", m, n, k, 1.0, 1.0, An, Bn, C0, c, m)
+
+
+def test_lu_trailing_update_shape(L):
+    """BASELINE config 5 (scaled down): A22 -= A21*A12 on sub-blocks of ONE matrix, lda=ldb=ldc (LU/PartialPivLU.h:492)."""
+    rng = np.random.default_rng(7)
+    N, bs = 1100, 64
+    M = oa.rand_matrix(rng, "d", N, N)
+    M0 = M.copy(order="F")
+    A21, A12, A22 = M[bs:, :bs], M[:bs, bs:], M[bs:, bs:]
+    mm = N - bs
+    r = eigen_b200.gemm_host("d", "N", "N", mm, mm, bs, -1.0, A21, N, A12, N, 1.0, A22, N)
+    assert r == 0
+    assert np.array_equal(M[:bs], M0[:bs]) and np.array_equal(M[:, :bs], M0[:, :bs])
+    ref, g = oa.hp_gemm("d", "N", "N", mm, mm, bs, -1.0, M0[bs:, :bs], N, M0[:bs, bs:], N, 1.0, M0[bs:, bs:], N)
+    assert (np.abs(M[bs:, bs:] - ref) / (oa.EPS["d"] * g)).max() < 16.0
