@@ -1,8 +1,457 @@
-// placeholder replaced below in this round: tcgen05 3xTF32 kernel
+// eigen_b200/csrc/gemm_tf32x3.cu -- float GEMM on the 5th-gen tensor cores with a 3xTF32 split (sm_100a).
+//
+// Replaces the reference's float path gemm_pack_lhs/rhs + gebp_kernel
+// (Eigen/src/Core/products/GeneralBlockPanelKernel.h:858-2105) for large sgemm products:
+//   * pack (the analogue of gemm_pack_lhs / gemm_pack_rhs, :1688-2105): one pass over op(A) (m x k) and op(B)^T
+//     (n x k) writes K-major panels split into hi = tf32(x) and lo = tf32(x - hi); the pass also canonicalises
+//     N/T/C and any lda/ldb, so the product kernel only ever sees 128-byte aligned K-major rows (TMA-legal);
+//   * product (the analogue of gebp_kernel, :858-1669): persistent, warp-specialised kernel -- warp 0 issues TMA
+//     (cp.async.bulk.tensor, SWIZZLE_128B) into a 2-stage shared-memory ring, one elected thread of warp 1 issues
+//     tcgen05.mma.kind::tf32 (M=128, N=256, K=8) three times per k-step -- lo*hi + hi*lo first, hi*hi last -- into
+//     a double-buffered 128x256 fp32 accumulator in TMEM, warps 2-5 drain TMEM with tcgen05.ld and apply
+//     C = alpha*acc + beta*C with coalesced column-major stores (the reference does beta in a separate pass,
+//     blas/level3_impl.h:62-66).  The dropped lo*lo term is O(2^-22 |a||b|) per product, below fp32 rounding.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace b200 {
-bool tf32x3_supported(const GemmProblem&) { return false; }
-size_t tf32x3_workspace_bytes(const GemmProblem&) { return 0; }
-int launch_tf32x3(const GemmProblem&, cudaStream_t, void*, size_t) { return (int)cudaErrorNotSupported; }
-double tf32_pipe_peak(int) { return -1.0; }
+namespace {
+
+constexpr int TM = 128, TN = 256, TK = 32, UK = 8, NSTAGE = 2;
+constexpr int A_PLANE = TM * TK * 4, B_PLANE = TN * TK * 4;
+constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // 98304
+constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+// ---------------- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 bytes apart (SBO); LBO unused
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;              // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;    // stride byte offset
+  d |= (uint64_t)1 << 46;              // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor, kind::tf32: D = f32, A = B = tf32, both K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------- pack: split op(X) into K-major tf32 hi / lo panels -----------------------------------------
+// element (r, kk) of the logical R x K operand lives at src[r*sr + kk*sk]; exactly one of sr, sk is 1.
+__global__ void __launch_bounds__(256)
+tf32_split_pack_kernel(const float* __restrict__ src, int64_t sr, int64_t sk, int64_t R, int64_t K,
+                       float* __restrict__ hi, float* __restrict__ lo, int64_t Kp) {
+  __shared__ float t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+  if (sk == 1) {
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t r = r0 + j, kk = k0 + tx;
+      t[j][tx] = (r < R && kk < K) ? src[r * sr + kk] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t kk = k0 + j, r = r0 + tx;
+      t[tx][j] = (r < R && kk < K) ? src[r + kk * sk] : 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j, kk = k0 + tx;
+    if (r < R && kk < Kp) {
+      const float x = t[j][tx];
+      uint32_t h, l;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+      const float res = x - __uint_as_float(h);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+      hi[r * Kp + kk] = __uint_as_float(h);
+      lo[r * Kp + kk] = __uint_as_float(l);
+    }
+  }
+}
+
+// ---------------- product ------------------------------------------------------------------------------------
+struct Tf32Params {
+  int64_t m, n, k;
+  float* C;
+  int64_t ldc;
+  float alpha, beta;
+  int beta_zero;
+  int64_t tiles_m, tiles_n;
+};
+
+constexpr int GROUP = 8;  // tile rasterisation: GROUP tile-rows per band (L2 reuse of the B panels)
+__device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t tiles_n, int64_t& tm, int64_t& tn) {
+  const int64_t per_group = GROUP * tiles_n;
+  const int64_t g = pid / per_group;
+  const int64_t first = g * GROUP;
+  const int64_t gsz = (tiles_m - first < GROUP) ? (tiles_m - first) : GROUP;
+  const int64_t in = pid - g * per_group;
+  tm = first + in % gsz;
+  tn = in / gsz;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                   const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                   const Tf32Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bars = base + NSTAGE * STAGE_BYTES;
+  // barrier map (8 bytes each): full[NSTAGE] | empty[NSTAGE] | tfull[2] | tempty[2] | tmem ptr (4 bytes)
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int64_t ntiles = p.tiles_m * p.tiles_n;
+  const int nkb = (int)((p.k + TK - 1) / TK);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t tm, tn;
+        tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        const int row_a = (int)(tm * TM), row_b = (int)(tn * TN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          mbar_expect_tx(full(stage), STAGE_BYTES);
+          const uint32_t s0 = base + stage * STAGE_BYTES;
+          tma_load_2d(s0, &mapAh, kb * TK, row_a, full(stage));
+          tma_load_2d(s0 + A_PLANE, &mapAl, kb * TK, row_a, full(stage));
+          tma_load_2d(s0 + 2 * A_PLANE, &mapBh, kb * TK, row_b, full(stage));
+          tma_load_2d(s0 + 2 * A_PLANE + B_PLANE, &mapBl, kb * TK, row_b, full(stage));
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer (single thread) =====
+      constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint32_t s0 = base + stage * STAGE_BYTES;
+          const uint64_t a_hi = umma_desc_sw128(s0), a_lo = umma_desc_sw128(s0 + A_PLANE);
+          const uint64_t b_hi = umma_desc_sw128(s0 + 2 * A_PLANE), b_lo = umma_desc_sw128(s0 + 2 * A_PLANE + B_PLANE);
+#pragma unroll
+          for (int k8 = 0; k8 < TK / UK; ++k8) {
+            const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);  // advance inside the 128-byte swizzle atom
+            tc_mma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | k8) != 0);
+            tc_mma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+            tc_mma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+          }
+          tc_commit(empty(stage));  // frees the smem stage once these MMAs have read it
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM -> registers -> C (alpha/beta fused) =====
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int64_t tm, tn;
+      tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const int64_t row = tm * TM + q * 32 + lane;
+      float* crow = p.C + row;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t)(acc * TN + c0) + ((uint32_t)(q * 32) << 16), r);
+        const int64_t col0 = tn * TN + c0;
+        if (row < p.m) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t col = col0 + j;
+            if (col < p.n) {
+              float v = p.alpha * __uint_as_float(r[j]);
+              float* pc = crow + col * p.ldc;
+              if (!p.beta_zero) v = fmaf(p.beta, *pc, v);
+              *pc = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------- TF32 pipe peak: back-to-back M=128 N=256 K=8 MMAs on zeroed shared memory ---------------------
+__global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bar = base + A_PLANE + B_PLANE;
+  const uint32_t tmem_slot = bar + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+  for (int i = threadIdx.x; i < (A_PLANE + B_PLANE) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(smem_raw + (base - raw))[i] = 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zero fill -> async-proxy MMA reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  if (warp == 0 && lane == 0) {
+    constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+    const uint64_t a = umma_desc_sw128(base), b = umma_desc_sw128(base + A_PLANE);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k8 = 0; k8 < 4; ++k8) tc_mma_tf32(tmem_base, a + 2 * k8, b + 2 * k8, idesc, (i | k8) != 0);
+    }
+    tc_commit(bar);
+    mbar_wait(bar, 0);
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(64) << 16), r);
+    if (r[lane] == 0x12345678u) out[0] = 1.f;  // keep the accumulator observable
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+  }
+}
+
+// ---------------- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return (EncodeTiledFn) nullptr;
+    if (q != cudaDriverEntryPointSuccess) return (EncodeTiledFn) nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// K-major panel: rows x K floats, row pitch Kp floats; box = 32 floats (128 bytes) x box_rows, SWIZZLE_128B
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t Kp, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return (int)cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)Kp * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+int64_t kpad(int64_t k) { return (k + 31) / 32 * 32; }
+int sm_count() {
+  static int sms = [] {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  return sms;
+}
+
+}  // namespace
+
+bool tf32x3_supported(const GemmProblem& p) {
+  if (p.type != TY_S) return false;
+  if (((uintptr_t)p.A & 3) || ((uintptr_t)p.B & 3) || ((uintptr_t)p.C & 3)) return false;
+  if (p.m <= 0 || p.n <= 0 || p.k <= 0) return false;
+  if (p.m > 0x7fffff00LL || p.n > 0x7fffff00LL || p.k > 0x7fffff00LL) return false;
+  return encode_fn() != nullptr;
+}
+
+size_t tf32x3_workspace_bytes(const GemmProblem& p) {
+  return (size_t)2 * (size_t)(p.m + p.n) * (size_t)kpad(p.k) * sizeof(float) + 1024;
+}
+
+int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t workspace_bytes) {
+  if (!workspace || workspace_bytes < tf32x3_workspace_bytes(p)) return (int)cudaErrorInvalidValue;
+  const int64_t Kp = kpad(p.k);
+  float* ws = (float*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  float* Ah = ws;
+  float* Al = Ah + p.m * Kp;
+  float* Bh = Al + p.m * Kp;
+  float* Bl = Bh + p.n * Kp;
+  // pack A: logical (i, kk) at A[i + kk*lda] ('N') or A[kk + i*lda] ('T'/'C'; conj is the identity for float)
+  {
+    dim3 grid((unsigned)(Kp / 32), (unsigned)((p.m + 31) / 32));
+    if (p.opa == OP_N) tf32_split_pack_kernel<<<grid, 256, 0, s>>>((const float*)p.A, 1, p.lda, p.m, p.k, Ah, Al, Kp);
+    else tf32_split_pack_kernel<<<grid, 256, 0, s>>>((const float*)p.A, p.lda, 1, p.m, p.k, Ah, Al, Kp);
+    count_launch();
+  }
+  // pack B^T: logical (j, kk) at B[kk + j*ldb] ('N') or B[j + kk*ldb] ('T'/'C')
+  {
+    dim3 grid((unsigned)(Kp / 32), (unsigned)((p.n + 31) / 32));
+    if (p.opb == OP_N) tf32_split_pack_kernel<<<grid, 256, 0, s>>>((const float*)p.B, p.ldb, 1, p.n, p.k, Bh, Bl, Kp);
+    else tf32_split_pack_kernel<<<grid, 256, 0, s>>>((const float*)p.B, 1, p.ldb, p.n, p.k, Bh, Bl, Kp);
+    count_launch();
+  }
+  B200_CUDA_TRY(cudaGetLastError());
+  CUtensorMap mAh, mAl, mBh, mBl;
+  if (make_map(&mAh, Ah, p.m, p.k, Kp, TM) || make_map(&mAl, Al, p.m, p.k, Kp, TM) ||
+      make_map(&mBh, Bh, p.n, p.k, Kp, TN) || make_map(&mBl, Bl, p.n, p.k, Kp, TN))
+    return (int)cudaErrorInvalidValue;
+  Tf32Params prm;
+  prm.m = p.m; prm.n = p.n; prm.k = p.k;
+  prm.C = (float*)p.C; prm.ldc = p.ldc;
+  prm.alpha = (float)p.alpha[0]; prm.beta = (float)p.beta[0];
+  prm.beta_zero = (p.beta[0] == 0.0);
+  prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + TN - 1) / TN;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t ntiles = prm.tiles_m * prm.tiles_n;
+  const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());  // persistent: one CTA per SM
+  note_variant("tf32x3_tcgen05_128x256x32");
+  tf32x3_gemm_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, prm);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+double tf32_pipe_peak(int millis) {
+  const int smem = A_PLANE + B_PLANE + 1024 + 64;
+  if (cudaFuncSetAttribute(tf32_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1.0;
+  float* out = nullptr;
+  if (cudaMalloc(&out, 64) != cudaSuccess) return -1.0;
+  const int iters = 4096, blocks = sm_count();
+  const double flops = (double)blocks * iters * 4.0 * 2.0 * TM * TN * UK;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  tf32_peak_kernel<<<blocks, 128, smem>>>(iters, out);
+  count_launch();
+  if (cudaDeviceSynchronize() != cudaSuccess) { cudaGetLastError(); cudaFree(out); return -1.0; }
+  double best = 0.0, total = 0.0;
+  while (total < millis) {
+    cudaEventRecord(e0);
+    tf32_peak_kernel<<<blocks, 128, smem>>>(iters, out);
+    count_launch();
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaGetLastError(); best = -1.0; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    total += ms;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}
+
+}  // namespace b200

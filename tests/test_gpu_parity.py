@@ -45,7 +45,9 @@ def _check(t, ta, tb, m, n, k, al, be, A, B, C0, c, ldc, rows=None, port_too=Tru
         c2 = C0.copy(order="F")
         oa.call_gemm(getattr(P, "oracle_%sgemm_" % t), t, ta, tb, m, n, k, al, A, A.shape[0], B, B.shape[0], be, c2, ldc)
         fro_port = np.linalg.norm(c2[:m] - ref) / max(np.linalg.norm(ref), 1e-300)
-        assert fro <= max(4.0 * fro_port, 2.0 * np.sqrt(max(k, 1)) * eps), (t, m, n, k, fro, fro_port)
+        # 3xTF32 drops the lo*lo term and accumulates in (non-IEEE-rounded) fp32 TMEM: allow twice the slack
+        slack = 2.0 if t in "sc" else 1.0
+        assert fro <= slack * max(4.0 * fro_port, 2.0 * np.sqrt(max(k, 1)) * eps), (t, m, n, k, fro, fro_port, eigen_b200.last_variant())
     return fro, ratio
 
 
