@@ -75,12 +75,27 @@ static int choose_variant(const GemmProblem& p, int requested) {
   return B200BLAS_SIMT;
 }
 
+// The pack workspace comes from the stream-ordered allocator; without a release threshold the pool hands its
+// memory back to the driver at every synchronisation and the next call pays for cudaMalloc again.
+static void keep_pool_memory() {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_dev) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done_dev = dev;
+}
+
 static int run_device(const GemmProblem& p, cudaStream_t s, int variant) {
   const int v = choose_variant(p, variant);
   if (v == B200BLAS_DMMA) return fail(launch_dmma(p, s));
   if (v == B200BLAS_TF32X3) {
     const size_t ws = tf32x3_workspace_bytes(p);
     void* w = nullptr;
+    keep_pool_memory();
     if (ws) { const int e = (int)cudaMallocAsync(&w, ws, s); if (e) return fail(e); }
     const int e = launch_tf32x3(p, s, w, ws);
     if (w) cudaFreeAsync(w, s);

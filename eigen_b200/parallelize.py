@@ -1,0 +1,249 @@
+"""Multi-GPU partitioner for the dense product -- the B200 counterpart of ``parallelize_gemm``.
+
+The reference splits ``C`` into one column slab per OpenMP thread (multiples of ``nr = 4`` columns), lets every
+thread read all of ``A`` and its own columns of ``B`` and packs ``A`` cooperatively
+(``Eigen/src/Core/products/Parallelizer.h:85-157``, ``GeneralMatrixMatrix.h:83-152``).  Here the workers are GPUs
+(one process each, ``torch.distributed`` over NCCL/NVLink): ``C`` is cut into a ``pr x pc`` grid of tiles, rank
+``(i, j)`` receives the row panel ``A_i`` and the column panel ``B_j`` and owns ``C_ij``; ``k`` is never split, so
+there is no reduction -- only panel distribution (broadcast / send) and the gather of the ``C`` tiles.
+
+Residency model of :class:`DistGemm.run`: ``A``, ``B``, ``C`` live on rank 0 ("root-resident", like the caller's
+matrices in the reference).  Pipeline on every rank:
+
+* phase 1 -- ``k`` is streamed in chunks: chunk ``c+1`` of ``A_i``/``B_j`` travels over NVLink (comm stream) while the
+  first column sub-slab of ``C_ij`` accumulates chunk ``c`` on the compute stream (``beta = 1`` after the first);
+  panels stay resident in HBM;
+* phase 2 -- the remaining column sub-slabs are single full-``k`` products; each finished sub-slab is sent to the root
+  while the next one computes; the root folds ``beta*C`` in when it stores the tile (``C_ij`` of the root itself
+  is computed in place).
+
+All tensors use the column-major convention of the BLAS seam: a ``rows x cols`` column-major matrix is held as a
+row-major torch tensor of shape ``(cols, rows)``.
+"""
+import os
+
+DEFAULT_GRIDS = {1: (1, 1), 2: (1, 2), 4: (1, 4), 8: (1, 8)}
+
+
+def grid_for(world):
+    """pr x pc process grid.  Default 1 x world (column slabs, exactly the reference's split, and the only cut for
+    which every panel of a column-major operand is contiguous); ``B200BLAS_GRID=2x4`` selects a 2-D grid."""
+    env = os.environ.get("B200BLAS_GRID")
+    if env:
+        pr, pc = (int(x) for x in env.lower().split("x"))
+        if pr * pc != world:
+            raise ValueError("B200BLAS_GRID=%s does not match world size %d" % (env, world))
+        return pr, pc
+    if world in DEFAULT_GRIDS:
+        return DEFAULT_GRIDS[world]
+    return 1, world
+
+
+def split(extent, parts, quantum):
+    """Cut [0, extent) into `parts` consecutive ranges whose lengths are multiples of `quantum` except the last,
+    which takes the remainder -- the rule of Parallelizer.h:140-151 (blockCols & ~3, blockRows rounded to mr) with
+    the CTA tile edge as quantum."""
+    block = -(-extent // parts)
+    block = -(-block // quantum) * quantum
+    out = []
+    for p in range(parts):
+        lo = min(extent, p * block)
+        hi = extent if p == parts - 1 else min(extent, (p + 1) * block)
+        out.append((lo, max(lo, hi)))
+    return out
+
+
+def partition(m, n, world, grid=None, quantum=128):
+    """Tile of C owned by each rank: list of (r0, r1, c0, c1), rank = i*pc + j."""
+    pr, pc = grid or grid_for(world)
+    rows, cols = split(m, pr, quantum), split(n, pc, quantum)
+    return [(rows[i][0], rows[i][1], cols[j][0], cols[j][1]) for i in range(pr) for j in range(pc)]
+
+
+def chunk_ranges(k, nchunks, quantum=256):
+    return [r for r in split(k, max(1, nchunks), quantum) if r[1] > r[0]]
+
+
+class DistGemm:
+    """C = alpha*A*B + beta*C across all ranks of the default process group (operands root-resident)."""
+
+    def __init__(self, t, m, n, k, alpha, beta, kchunks=8, subslabs=4, grid=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.t, self.m, self.n, self.k, self.alpha, self.beta = t, m, n, k, alpha, beta
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.pr, self.pc = grid or grid_for(self.world)
+        self.i, self.j = divmod(self.rank, self.pc)
+        self.tiles = partition(m, n, self.world, (self.pr, self.pc))
+        self.r0, self.r1, self.c0, self.c1 = self.tiles[self.rank]
+        self.mi, self.nj = self.r1 - self.r0, self.c1 - self.c0
+        self.chunks = chunk_ranges(k, kchunks)
+        self.sub = [(a + self.c0, b + self.c0) for a, b in split(self.nj, max(1, subslabs), 128) if b > a]
+        self.dtype = {"s": torch.float32, "d": torch.float64, "c": torch.complex64, "z": torch.complex128}[t]
+        self.backend = dist.get_backend()
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
+        import eigen_b200
+        self.gemm = eigen_b200.gemm_dev  # the sm_100a library; there is no other implementation
+        # sub-communicators: grid rows share A_i, grid columns share B_j (every rank creates every group)
+        self.row_groups, self.col_groups = [], []
+        for i in range(self.pr):
+            ranks = [i * self.pc + j for j in range(self.pc)]
+            self.row_groups.append(dist.new_group(ranks) if self.pc > 1 and self.pr > 1 else None)
+        for j in range(self.pc):
+            ranks = [i * self.pc + j for i in range(self.pr)]
+            self.col_groups.append(dist.new_group(ranks) if self.pr > 1 and self.pc > 1 else None)
+        is_root = self.rank == 0
+        kw = dict(dtype=self.dtype, device=self.dev)
+        # resident panels (column-major mi x k and k x nj); the root reads its own panels straight from A and B
+        self.Ai = None if is_root else torch.empty(k, self.mi, **kw)
+        self.Bj = None if is_root else [torch.empty(self.nj, ck[1] - ck[0], **kw) for ck in self.chunks]
+        self.P = None if is_root else torch.empty(self.nj, self.mi, **kw)
+        self.recv = None
+        if is_root:
+            self.recv = {r: torch.empty(tl[3] - tl[2], tl[1] - tl[0], **kw) for r, tl in enumerate(self.tiles) if r != 0}
+        if self.dev.type == "cuda":
+            self.comm = torch.cuda.Stream()
+            self.out = torch.cuda.Stream()
+        else:
+            self.comm = self.out = None
+
+    # -- helpers ------------------------------------------------------------------------------------------------
+    def _on(self, stream):
+        import contextlib
+        return self.torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def _event(self, stream=None):
+        if self.dev.type != "cuda":
+            return None
+        e = self.torch.cuda.Event()
+        e.record(stream if stream is not None else self.torch.cuda.current_stream())
+        return e
+
+    def _wait(self, stream, ev):
+        if ev is not None:
+            (stream if stream is not None else self.torch.cuda.current_stream()).wait_event(ev)
+
+    def _distribute_chunk(self, A, B, ci):
+        """Move chunk ci of every rank's panels (comm stream).  Collective order is identical on all ranks."""
+        dist = self.dist
+        k0, k1 = self.chunks[ci]
+        # ---- A row panels: At[k0:k1, r0:r1] ----
+        if self.pr == 1:
+            buf = A[k0:k1] if self.rank == 0 else self.Ai[k0:k1]   # contiguous (kc, m): no packing needed
+            dist.broadcast(buf, src=0)
+        else:
+            for i in range(self.pr):
+                leader = i * self.pc
+                rows = split(self.m, self.pr, 128)[i]
+                if self.rank == 0 and leader != 0:
+                    dist.send(A[k0:k1, rows[0]:rows[1]].contiguous(), dst=leader)
+                elif self.rank == leader and leader != 0:
+                    dist.recv(self.Ai[k0:k1], src=0)
+                if self.i == i and self.pc > 1:
+                    if self.rank == 0:
+                        buf = A[k0:k1, rows[0]:rows[1]].contiguous()
+                    else:
+                        buf = self.Ai[k0:k1]
+                    dist.broadcast(buf, src=leader, group=self.row_groups[i])
+        # ---- B column panels: Bt[c0:c1, k0:k1] ----
+        for j in range(self.pc):
+            leader = j
+            cols = split(self.n, self.pc, 128)[j]
+            if self.pc == 1:
+                buf = B[:, k0:k1].contiguous() if self.rank == 0 else self.Bj[ci]
+                dist.broadcast(buf, src=0)
+                continue
+            if self.rank == 0 and leader != 0:
+                dist.send(B[cols[0]:cols[1], k0:k1].contiguous(), dst=leader)
+            elif self.rank == leader and leader != 0:
+                dist.recv(self.Bj[ci], src=0)
+            if self.j == j and self.pr > 1:
+                if self.rank == 0:
+                    buf = B[cols[0]:cols[1], k0:k1].contiguous()
+                else:
+                    buf = self.Bj[ci]
+                dist.broadcast(buf, src=leader, group=self.col_groups[j])
+
+    def _local(self, A, B, C, cols, ks, first):
+        """One local product on this rank's tile: columns `cols` (global), k range `ks`."""
+        c0, c1 = cols
+        k0, k1 = ks
+        nn, kk = c1 - c0, k1 - k0
+        if nn <= 0 or self.mi <= 0:
+            return
+        if self.rank == 0:
+            # operands and the C tile in place inside the caller's matrices (ld = m / k / m)
+            a = A[k0:k1, self.r0:]
+            b = B[c0:c1, k0:]
+            c = C[c0:c1, self.r0:]
+            beta = self.beta if first else 1.0
+            self.gemm(self.t, "N", "N", self.mi, nn, kk, self.alpha, a, self.m, b, self.k, beta, c, self.m)
+        else:
+            a = self.Ai[k0:k1]
+            c = self.P[c0 - self.c0:c1 - self.c0]
+            beta = 0.0 if first else 1.0
+            if (k0, k1) == (0, self.k):
+                # full-k product: B_j is stored per chunk -> accumulate chunk by chunk
+                for ci, (q0, q1) in enumerate(self.chunks):
+                    b = self.Bj[ci][c0 - self.c0:c1 - self.c0]
+                    self.gemm(self.t, "N", "N", self.mi, nn, q1 - q0, self.alpha, self.Ai[q0:q1], self.mi, b, q1 - q0,
+                              0.0 if ci == 0 else 1.0, c, self.mi)
+            else:
+                ci = self.chunks.index((k0, k1))
+                b = self.Bj[ci][c0 - self.c0:c1 - self.c0]
+                self.gemm(self.t, "N", "N", self.mi, nn, kk, self.alpha, a, self.mi, b, kk, beta, c, self.mi)
+
+    # -- the product ----------------------------------------------------------------------------------------------
+    def run(self, A=None, B=None, C=None):
+        """A: (k, m), B: (n, k), C: (n, m) torch tensors on rank 0 (None elsewhere).  C is updated in place."""
+        torch, dist = self.torch, self.dist
+        cur = torch.cuda.current_stream() if self.dev.type == "cuda" else None
+        start = self._event(cur)
+        self._wait(self.comm, start)
+        self._wait(self.out, start)
+        ready = []
+        # phase 1: stream k chunks; first sub-slab accumulates as chunks land
+        for ci in range(len(self.chunks)):
+            with self._on(self.comm):
+                self._distribute_chunk(A, B, ci)
+                ready.append(self._event(self.comm))
+        for ci, ks in enumerate(self.chunks):
+            self._wait(cur, ready[ci])
+            if self.sub:
+                self._local(A, B, C, self.sub[0], ks, ci == 0)
+        sends = []
+        if self.sub:
+            sends.append((0, self._event(cur)))
+        # phase 2: remaining sub-slabs, full k
+        for si in range(1, len(self.sub)):
+            self._local(A, B, C, self.sub[si], (0, self.k), True)
+            sends.append((si, self._event(cur)))
+        # gather: every finished sub-slab goes to the root on the out stream while the next one computes
+        with self._on(self.out):
+            for si, ev in sends:
+                self._wait(self.out, ev)
+                if self.rank != 0:
+                    c0, c1 = self.sub[si]
+                    dist.send(self.P[c0 - self.c0:c1 - self.c0], dst=0)
+                else:
+                    for r, tl in enumerate(self.tiles):
+                        if r == 0:
+                            continue
+                        subs = [(a + tl[2], b + tl[2]) for a, b in split(tl[3] - tl[2], max(1, len(self.sub)), 128) if b > a]
+                        if si >= len(subs):
+                            continue
+                        s0, s1 = subs[si]
+                        buf = self.recv[r][s0 - tl[2]:s1 - tl[2]]
+                        dist.recv(buf, src=r)
+                        dst = C[s0:s1, tl[0]:tl[1]]
+                        if self.beta == 0:
+                            dst.copy_(buf)
+                        else:
+                            if self.beta != 1:
+                                dst.mul_(self.beta)
+                            dst.add_(buf)
+            fin = self._event(self.out)
+        self._wait(cur, fin)
+        if self.comm is not None:
+            cur.wait_stream(self.comm)

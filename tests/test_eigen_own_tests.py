@@ -1,0 +1,32 @@
+"""The reference's OWN product unit tests (test/product_{large,extra,small,notemporary}.cpp), compiled unmodified
+with -DEIGEN_USE_BLAS by oracle/Makefile (target eigen_tests) and linked against libb200blas.so: every Eigen
+`A*B` in them reaches our ?gemm_ through GeneralMatrixMatrix_BLAS.h:103.  Needs a B200 (the binaries abort through
+xerbla_ info=-1 otherwise: there is no CPU fallback)."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _run(name, variant, seed):
+    exe = os.path.join(BIN, "eigen_test_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/eigen_test_%s not built (make -C oracle eigen_tests needs /root/reference)" % name)
+    env = dict(os.environ)
+    env.pop("B200BLAS_VARIANT", None)
+    if variant != "auto":
+        env["B200BLAS_VARIANT"] = variant
+    # r<repeat> s<seed>: test/main.h:136,766-780
+    p = subprocess.run([exe, "r3", "s%d" % seed], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900, text=True)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert "ERROR #-1" not in p.stdout, "a CUDA failure was reported through xerbla_"
+
+
+@pytest.mark.parametrize("variant", ["auto", "dmma", "tf32x3"])
+@pytest.mark.parametrize("name", ["product_large", "product_extra", "product_small"])
+def test_eigen_product_tests_pass_on_the_gpu_library(name, variant):
+    _run(name, variant, 12345)
