@@ -276,6 +276,221 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   }
 }
 
+// ---------------- complex<float>: same machinery on de-interleaved planes ---------------------------------------
+// C = A*B with A = Ar + i Ai, B = Br + i Bi:  Re = Ar.Br - Ai.Bi,  Im = Ar.Bi + Ai.Br  (the four real products of
+// the reference's complex gebp, GeneralBlockPanelKernel.h:566-744), each as a 3xTF32 product; the minus sign is the
+// negate-A bit of the instruction descriptor; conjugation is folded in at pack time (conj_if, BlasUtil.h:43-124).
+// Tile: 128 complex rows x 64 complex columns; TMEM holds Re (64 cols) and Im (64 cols), double buffered.
+constexpr int CTN = 64;
+constexpr int CB_PLANE = CTN * TK * 4;                       // 8192
+constexpr int CSTAGE_BYTES = 4 * A_PLANE + 4 * CB_PLANE;     // 98304
+constexpr int CSMEM_BYTES = NSTAGE * CSTAGE_BYTES + 1024 + 256;
+constexpr int CTMEM_COLS = 256;
+
+__global__ void __launch_bounds__(256)
+tf32_split_pack_cplx_kernel(const float2* __restrict__ src, int64_t sr, int64_t sk, int64_t R, int64_t K, int conj,
+                            float* __restrict__ re_hi, float* __restrict__ re_lo, float* __restrict__ im_hi,
+                            float* __restrict__ im_lo, int64_t Kp) {
+  __shared__ float2 t[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t r0 = (int64_t)blockIdx.y * 32, k0 = (int64_t)blockIdx.x * 32;
+  if (sk == 1) {
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t r = r0 + j, kk = k0 + tx;
+      t[j][tx] = (r < R && kk < K) ? src[r * sr + kk] : make_float2(0.f, 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+      const int64_t kk = k0 + j, r = r0 + tx;
+      t[tx][j] = (r < R && kk < K) ? src[r + kk * sk] : make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j, kk = k0 + tx;
+    if (r < R && kk < Kp) {
+      float2 x = t[j][tx];
+      if (conj) x.y = -x.y;
+      uint32_t h, l;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x.x));
+      float res = x.x - __uint_as_float(h);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+      re_hi[r * Kp + kk] = __uint_as_float(h);
+      re_lo[r * Kp + kk] = __uint_as_float(l);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x.y));
+      res = x.y - __uint_as_float(h);
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+      im_hi[r * Kp + kk] = __uint_as_float(h);
+      im_lo[r * Kp + kk] = __uint_as_float(l);
+    }
+  }
+}
+
+struct CMaps { CUtensorMap a[4], b[4]; };  // plane order: re_hi, re_lo, im_hi, im_lo
+struct CTf32Params {
+  int64_t m, n, k;
+  float2* C;
+  int64_t ldc;
+  float2 alpha, beta;
+  int beta_zero;
+  int64_t tiles_m, tiles_n;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + NSTAGE * CSTAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[i])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b[i])) : "memory");
+    }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(CTMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int64_t ntiles = p.tiles_m * p.tiles_n;
+  const int nkb = (int)((p.k + TK - 1) / TK);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer: 8 planes per stage =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t tm, tn;
+        tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        const int row_a = (int)(tm * TM), row_b = (int)(tn * CTN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          mbar_expect_tx(full(stage), CSTAGE_BYTES);
+          const uint32_t s0 = base + stage * CSTAGE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_2d(s0 + i * A_PLANE, &maps.a[i], kb * TK, row_a, full(stage));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tma_load_2d(s0 + 4 * A_PLANE + i * CB_PLANE, &maps.b[i], kb * TK, row_b, full(stage));
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_tf32(TM, CTN);
+      constexpr uint32_t idesc_neg = idesc | (1u << 13);  // negate A
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(tempty(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_re = tmem_base + (uint32_t)(acc * 2 * CTN), d_im = d_re + CTN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint32_t s0 = base + stage * CSTAGE_BYTES;
+          uint64_t a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { a[i] = umma_desc_sw128(s0 + i * A_PLANE); b[i] = umma_desc_sw128(s0 + 4 * A_PLANE + i * CB_PLANE); }
+          // index: 0 = re_hi, 1 = re_lo, 2 = im_hi, 3 = im_lo
+#pragma unroll
+          for (int k8 = 0; k8 < TK / UK; ++k8) {
+            const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);
+            const uint32_t first = (kb | k8) != 0;
+            // Re += Ar.Br
+            tc_mma_tf32(d_re, a[1] + off, b[0] + off, idesc, first);
+            tc_mma_tf32(d_re, a[0] + off, b[1] + off, idesc, 1u);
+            tc_mma_tf32(d_re, a[0] + off, b[0] + off, idesc, 1u);
+            // Re -= Ai.Bi
+            tc_mma_tf32(d_re, a[3] + off, b[2] + off, idesc_neg, 1u);
+            tc_mma_tf32(d_re, a[2] + off, b[3] + off, idesc_neg, 1u);
+            tc_mma_tf32(d_re, a[2] + off, b[2] + off, idesc_neg, 1u);
+            // Im += Ar.Bi
+            tc_mma_tf32(d_im, a[1] + off, b[2] + off, idesc, first);
+            tc_mma_tf32(d_im, a[0] + off, b[3] + off, idesc, 1u);
+            tc_mma_tf32(d_im, a[0] + off, b[2] + off, idesc, 1u);
+            // Im += Ai.Br
+            tc_mma_tf32(d_im, a[3] + off, b[0] + off, idesc, 1u);
+            tc_mma_tf32(d_im, a[2] + off, b[1] + off, idesc, 1u);
+            tc_mma_tf32(d_im, a[2] + off, b[0] + off, idesc, 1u);
+          }
+          tc_commit(empty(stage));
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int64_t tm, tn;
+      tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const int64_t row = tm * TM + q * 32 + lane;
+      float2* crow = p.C + row;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CTN; c0 += 32) {
+        uint32_t re[32], im[32];
+        const uint32_t t0 = tmem_base + (uint32_t)(acc * 2 * CTN + c0) + ((uint32_t)(q * 32) << 16);
+        tmem_ld32(t0, re);
+        tmem_ld32(t0 + CTN, im);
+        const int64_t col0 = tn * CTN + c0;
+        if (row < p.m) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t col = col0 + j;
+            if (col < p.n) {
+              const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+              float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
+              float2* pc = crow + col * p.ldc;
+              if (!p.beta_zero) {
+                const float2 o = *pc;
+                v.x += fmaf(p.beta.x, o.x, -p.beta.y * o.y);
+                v.y += fmaf(p.beta.x, o.y, p.beta.y * o.x);
+              }
+              *pc = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CTMEM_COLS) : "memory");
+  }
+}
+
 // ---------------- TF32 pipe peak: back-to-back M=128 N=256 K=8 MMAs on zeroed shared memory ---------------------
 __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, float* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -367,21 +582,67 @@ int sm_count() {
 }  // namespace
 
 bool tf32x3_supported(const GemmProblem& p) {
-  if (p.type != TY_S) return false;
-  if (((uintptr_t)p.A & 3) || ((uintptr_t)p.B & 3) || ((uintptr_t)p.C & 3)) return false;
+  if (p.type != TY_S && p.type != TY_C) return false;
+  const uintptr_t am = p.type == TY_C ? 7 : 3;
+  if (((uintptr_t)p.A & am) || ((uintptr_t)p.B & am) || ((uintptr_t)p.C & am)) return false;
   if (p.m <= 0 || p.n <= 0 || p.k <= 0) return false;
   if (p.m > 0x7fffff00LL || p.n > 0x7fffff00LL || p.k > 0x7fffff00LL) return false;
   return encode_fn() != nullptr;
 }
 
 size_t tf32x3_workspace_bytes(const GemmProblem& p) {
-  return (size_t)2 * (size_t)(p.m + p.n) * (size_t)kpad(p.k) * sizeof(float) + 1024;
+  const size_t planes = p.type == TY_C ? 4 : 2;
+  return planes * (size_t)(p.m + p.n) * (size_t)kpad(p.k) * sizeof(float) + 1024;
+}
+
+static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
+  const int64_t Kp = kpad(p.k);
+  float* ap[4];
+  float* bp[4];
+  for (int i = 0; i < 4; ++i) ap[i] = ws + (int64_t)i * p.m * Kp;
+  for (int i = 0; i < 4; ++i) bp[i] = ws + 4 * p.m * Kp + (int64_t)i * p.n * Kp;
+  {
+    dim3 grid((unsigned)(Kp / 32), (unsigned)((p.m + 31) / 32));
+    if (p.opa == OP_N) tf32_split_pack_cplx_kernel<<<grid, 256, 0, s>>>((const float2*)p.A, 1, p.lda, p.m, p.k, 0, ap[0], ap[1], ap[2], ap[3], Kp);
+    else tf32_split_pack_cplx_kernel<<<grid, 256, 0, s>>>((const float2*)p.A, p.lda, 1, p.m, p.k, p.opa == OP_C, ap[0], ap[1], ap[2], ap[3], Kp);
+    count_launch();
+  }
+  {
+    dim3 grid((unsigned)(Kp / 32), (unsigned)((p.n + 31) / 32));
+    if (p.opb == OP_N) tf32_split_pack_cplx_kernel<<<grid, 256, 0, s>>>((const float2*)p.B, p.ldb, 1, p.n, p.k, 0, bp[0], bp[1], bp[2], bp[3], Kp);
+    else tf32_split_pack_cplx_kernel<<<grid, 256, 0, s>>>((const float2*)p.B, 1, p.ldb, p.n, p.k, p.opb == OP_C, bp[0], bp[1], bp[2], bp[3], Kp);
+    count_launch();
+  }
+  B200_CUDA_TRY(cudaGetLastError());
+  CMaps maps;
+  for (int i = 0; i < 4; ++i) {
+    if (make_map(&maps.a[i], ap[i], p.m, p.k, Kp, TM) || make_map(&maps.b[i], bp[i], p.n, p.k, Kp, CTN)) return (int)cudaErrorInvalidValue;
+  }
+  CTf32Params prm;
+  prm.m = p.m; prm.n = p.n; prm.k = p.k;
+  prm.C = (float2*)p.C; prm.ldc = p.ldc;
+  prm.alpha = make_float2((float)p.alpha[0], (float)p.alpha[1]);
+  prm.beta = make_float2((float)p.beta[0], (float)p.beta[1]);
+  prm.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
+  prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + CTN - 1) / CTN;
+  static bool attr_done = false;
+  if (!attr_done) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM_BYTES));
+    attr_done = true;
+  }
+  const int64_t ntiles = prm.tiles_m * prm.tiles_n;
+  const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
+  note_variant("tf32x3_tcgen05_c_128x64x32");
+  tf32x3_cgemm_kernel<<<grid, THREADS, CSMEM_BYTES, s>>>(maps, prm);
+  count_launch();
+  return (int)cudaGetLastError();
 }
 
 int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t workspace_bytes) {
   if (!workspace || workspace_bytes < tf32x3_workspace_bytes(p)) return (int)cudaErrorInvalidValue;
   const int64_t Kp = kpad(p.k);
   float* ws = (float*)(((uintptr_t)workspace + 1023) & ~(uintptr_t)1023);
+  if (p.type == TY_C) return launch_tf32x3_cplx(p, s, ws);
   float* Ah = ws;
   float* Al = Ah + p.m * Kp;
   float* Bh = Al + p.m * Kp;
