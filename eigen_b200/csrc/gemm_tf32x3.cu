@@ -132,7 +132,7 @@ struct Tf32Params {
   int64_t tiles_m, tiles_n;
 };
 
-constexpr int GROUP = 8;  // tile rasterisation: GROUP tile-rows per band (L2 reuse of the B panels)
+constexpr int GROUP = 16;  // tile rasterisation: a wave of 148 tiles covers ~16 x 9 tiles (2048 x 2304 of C): balanced A/B panel reuse in L2
 __device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t tiles_n, int64_t& tm, int64_t& tn) {
   const int64_t per_group = GROUP * tiles_n;
   const int64_t g = pid / per_group;

@@ -135,7 +135,8 @@ struct Staging {
   void* dbuf[3] = {nullptr, nullptr, nullptr};
   size_t dcap[3] = {0, 0, 0};
   static constexpr int MAX_SLABS = 64;
-  cudaEvent_t ev_in[MAX_SLABS], ev_comp[MAX_SLABS], ev_a = nullptr;
+  static constexpr int MAX_ACHUNKS = 8;
+  cudaEvent_t ev_in[MAX_SLABS], ev_comp[MAX_SLABS], ev_ac[MAX_ACHUNKS], ev_a = nullptr;
   bool ready = false;
 
   int init() {
@@ -152,6 +153,7 @@ struct Staging {
       B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
       B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < MAX_ACHUNKS; ++i) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_ac[i], cudaEventDisableTiming));
     ready = true;
     return 0;
   }
@@ -170,6 +172,7 @@ struct Staging {
     if (s_out) cudaStreamDestroy(s_out);
     if (ev_a) cudaEventDestroy(ev_a);
     for (int i = 0; i < MAX_SLABS; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); }
+    for (int i = 0; i < MAX_ACHUNKS; ++i) cudaEventDestroy(ev_ac[i]);
     s_in = s_comp = s_out = nullptr; ev_a = nullptr;
     ready = false;
   }
@@ -217,13 +220,26 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
   int nslabs = (int)((n + slab - 1) / slab);
   if (nslabs > Staging::MAX_SLABS) { slab = round_up((n + Staging::MAX_SLABS - 1) / Staging::MAX_SLABS, 256); nslabs = (int)((n + slab - 1) / slab); }
 
-  if (have_product) {
-    B200_CUDA_TRY(cudaMemcpy2DAsync(dA, (size_t)dlda * es, a, (size_t)lda * es, (size_t)ra * es, (size_t)ca,
-                                    cudaMemcpyHostToDevice, st.s_in));
-    t_h2d += (uint64_t)ra * ca * es;
-    B200_CUDA_TRY(cudaEventRecord(st.ev_a, st.s_in));
-    B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_a, 0));
-  }
+  // A travels in k-chunks (contiguous column blocks for 'N', row blocks for 'T'/'C'); the first column slab of C
+  // accumulates chunk by chunk (beta = 1 after the first) while later chunks are still on the bus, so the
+  // start-up bubble is one chunk instead of all of A.  Later slabs see A resident and run at full k.
+  int nac = 1;
+  if (have_product && nslabs > 1 && k >= 8 * 512) nac = Staging::MAX_ACHUNKS;
+  const int64_t kch = round_up((k + nac - 1) / nac, 256);
+  auto upload_a_chunk = [&](int c) -> int {
+    const int64_t k0 = (int64_t)c * kch, kc = std::min<int64_t>(kch, k - k0);
+    if (kc <= 0) return 0;
+    if (opa == OP_N) {
+      B200_CUDA_TRY(cudaMemcpy2DAsync(dA + (size_t)k0 * dlda * es, (size_t)dlda * es, (const char*)a + (size_t)k0 * lda * es,
+                                      (size_t)lda * es, (size_t)m * es, (size_t)kc, cudaMemcpyHostToDevice, st.s_in));
+    } else {
+      B200_CUDA_TRY(cudaMemcpy2DAsync(dA + (size_t)k0 * es, (size_t)dlda * es, (const char*)a + (size_t)k0 * es,
+                                      (size_t)lda * es, (size_t)kc * es, (size_t)m, cudaMemcpyHostToDevice, st.s_in));
+    }
+    t_h2d += (uint64_t)m * kc * es;
+    B200_CUDA_TRY(cudaEventRecord(st.ev_ac[c], st.s_in));
+    return 0;
+  };
   for (int j = 0; j < nslabs; ++j) {
     const int64_t j0 = (int64_t)j * slab, nj = std::min<int64_t>(slab, n - j0);
     if (have_product) {
@@ -249,7 +265,23 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
     p.A = dA; p.lda = dlda;
     p.B = (opb == OP_N) ? dB + (size_t)j0 * dldb * es : dB + (size_t)j0 * es; p.ldb = dldb;
     p.C = dC + (size_t)j0 * dldc * es; p.ldc = dldc;
-    { const int e = run_device(p, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
+    if (j == 0 && have_product) {
+      for (int cix = 0; cix < nac; ++cix) {
+        const int64_t k0 = (int64_t)cix * kch, kc = std::min<int64_t>(kch, k - k0);
+        if (kc <= 0) break;
+        { const int e = upload_a_chunk(cix); if (e) return e; }
+        B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_ac[cix], 0));
+        GemmProblem q = p;
+        q.k = kc;
+        q.A = (opa == OP_N) ? dA + (size_t)k0 * dlda * es : dA + (size_t)k0 * es;
+        q.B = (opb == OP_N) ? (const char*)p.B + (size_t)k0 * es : (const char*)p.B + (size_t)k0 * dldb * es;
+        if (cix > 0) { q.beta[0] = 1.0; q.beta[1] = 0.0; }
+        { const int e = run_device(q, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
+      }
+    } else {
+      const int e = run_device(p, st.s_comp, B200BLAS_AUTO);
+      if (e) { cudaDeviceSynchronize(); return e; }
+    }
     B200_CUDA_TRY(cudaEventRecord(st.ev_comp[j], st.s_comp));
     B200_CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_comp[j], 0));
     // only the m x nj window travels back: rows m..ldc-1 of the caller's C stay untouched
