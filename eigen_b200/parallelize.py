@@ -97,7 +97,11 @@ class DistGemm:
         kw = dict(dtype=self.dtype, device=self.dev)
         # resident panels (column-major mi x k and k x nj); the root reads its own panels straight from A and B
         self.Ai = None if is_root else torch.empty(k, self.mi, **kw)
-        self.Bj = None if is_root else [torch.empty(self.nj, ck[1] - ck[0], **kw) for ck in self.chunks]
+        # B_j is assembled as ONE column-major k x nj panel (ld = k) so that phase 2 is a single full-k launch per
+        # sub-slab; NCCL needs contiguous buffers, so chunks land in a small staging pair and are copied into place
+        self.Bj = None if is_root else torch.empty(self.nj, k, **kw)
+        kmax = max(c[1] - c[0] for c in self.chunks)
+        self.Bstage = None if is_root else [torch.empty(self.nj * kmax, **kw) for _ in range(2)]
         self.P = None if is_root else torch.empty(self.nj, self.mi, **kw)
         self.recv = None
         if is_root:
@@ -150,20 +154,22 @@ class DistGemm:
         for j in range(self.pc):
             leader = j
             cols = split(self.n, self.pc, 128)[j]
+            stage = None
+            if self.rank != 0 and self.j == j:
+                stage = self.Bstage[ci % 2][:self.nj * (k1 - k0)].view(self.nj, k1 - k0)
             if self.pc == 1:
-                buf = B[:, k0:k1].contiguous() if self.rank == 0 else self.Bj[ci]
+                buf = B[:, k0:k1].contiguous() if self.rank == 0 else stage
                 dist.broadcast(buf, src=0)
-                continue
-            if self.rank == 0 and leader != 0:
-                dist.send(B[cols[0]:cols[1], k0:k1].contiguous(), dst=leader)
-            elif self.rank == leader and leader != 0:
-                dist.recv(self.Bj[ci], src=0)
-            if self.j == j and self.pr > 1:
-                if self.rank == 0:
-                    buf = B[cols[0]:cols[1], k0:k1].contiguous()
-                else:
-                    buf = self.Bj[ci]
-                dist.broadcast(buf, src=leader, group=self.col_groups[j])
+            else:
+                if self.rank == 0 and leader != 0:
+                    dist.send(B[cols[0]:cols[1], k0:k1].contiguous(), dst=leader)
+                elif self.rank == leader and leader != 0:
+                    dist.recv(stage, src=0)
+                if self.j == j and self.pr > 1:
+                    buf = B[cols[0]:cols[1], k0:k1].contiguous() if self.rank == 0 else stage
+                    dist.broadcast(buf, src=leader, group=self.col_groups[j])
+            if stage is not None:
+                self.Bj[:, k0:k1].copy_(stage)   # strided device copy on the comm stream
 
     def _local(self, A, B, C, cols, ks, first):
         """One local product on this rank's tile: columns `cols` (global), k range `ks`."""
@@ -181,18 +187,10 @@ class DistGemm:
             self.gemm(self.t, "N", "N", self.mi, nn, kk, self.alpha, a, self.m, b, self.k, beta, c, self.m)
         else:
             a = self.Ai[k0:k1]
+            b = self.Bj[c0 - self.c0:c1 - self.c0, k0:]
             c = self.P[c0 - self.c0:c1 - self.c0]
             beta = 0.0 if first else 1.0
-            if (k0, k1) == (0, self.k):
-                # full-k product: B_j is stored per chunk -> accumulate chunk by chunk
-                for ci, (q0, q1) in enumerate(self.chunks):
-                    b = self.Bj[ci][c0 - self.c0:c1 - self.c0]
-                    self.gemm(self.t, "N", "N", self.mi, nn, q1 - q0, self.alpha, self.Ai[q0:q1], self.mi, b, q1 - q0,
-                              0.0 if ci == 0 else 1.0, c, self.mi)
-            else:
-                ci = self.chunks.index((k0, k1))
-                b = self.Bj[ci][c0 - self.c0:c1 - self.c0]
-                self.gemm(self.t, "N", "N", self.mi, nn, kk, self.alpha, a, self.mi, b, kk, beta, c, self.mi)
+            self.gemm(self.t, "N", "N", self.mi, nn, kk, self.alpha, a, self.mi, b, self.k, beta, c, self.mi)
 
     # -- the product ----------------------------------------------------------------------------------------------
     def run(self, A=None, B=None, C=None):
