@@ -206,7 +206,8 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)  # NCCL kernels must not queue behind GEMM CTAs
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
     L = eigen_b200.require_device()
     t, m, n, k, alpha, beta = WORKLOADS[args.workload]
     dt = torch_dtype(t)

@@ -13,6 +13,8 @@
 //     blas/level3_impl.h:62-66).  The dropped lo*lo term is O(2^-22 |a||b|) per product, below fp32 rounding.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b200 {
@@ -266,6 +268,161 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------- 256x256 tile variant (large k): 1.5x less L2->SM traffic per flop ------------------------------
+// The 128x256 kernel above needs 64 B/clk/SM of operands at full tensor rate, more than L2 delivers (~42 B/clk/SM):
+// ncu shows it operand-starved at ~65-78 % tensor-pipe activity.  Here one CTA owns a 256x256 tile of C as two
+// 128x256 accumulators that fill all 512 TMEM columns (no TMEM double buffering: the epilogue of a tile is < 3 % of
+// its main loop once k >= 2048), every B k-block is used by both halves, and the stage shrinks to
+// TK2 = 16 floats (64-byte rows, SWIZZLE_64B) so that three 64 KB stages fit: 42 B/clk/SM.
+constexpr int TM2 = 256, TK2 = 16, NSTAGE2 = 3;
+constexpr int PLANE2 = 256 * TK2 * 4;                 // 16384: one 256-row hi or lo plane of A or B
+constexpr int STAGE2_BYTES = 4 * PLANE2;              // 65536
+constexpr int SMEM2_BYTES = NSTAGE2 * STAGE2_BYTES + 1024 + 256;
+
+// K-major operand, 64-byte rows, SWIZZLE_64B: 8-row groups are 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;  // SWIZZLE_64B
+  return d;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tf32x3_gemm256_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                      const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                      const Tf32Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + NSTAGE2 * STAGE2_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (NSTAGE2 + s); };
+  const uint32_t tfull = bars + 8u * (2 * NSTAGE2), tempty = bars + 8u * (2 * NSTAGE2 + 1);
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE2 + 2);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+    for (int s = 0; s < NSTAGE2; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int64_t ntiles = p.tiles_m * p.tiles_n;
+  const int nkb = (int)((p.k + TK2 - 1) / TK2);
+
+  if (warp == 0) {
+    if (lane == 0) {  // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t tm, tn;
+        tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        const int row_a = (int)(tm * TM2), row_b = (int)(tn * TN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1u);
+          mbar_expect_tx(full(stage), STAGE2_BYTES);
+          const uint32_t s0 = base + stage * STAGE2_BYTES;
+          tma_load_2d(s0, &mapAh, kb * TK2, row_a, full(stage));
+          tma_load_2d(s0 + PLANE2, &mapAl, kb * TK2, row_a, full(stage));
+          tma_load_2d(s0 + 2 * PLANE2, &mapBh, kb * TK2, row_b, full(stage));
+          tma_load_2d(s0 + 3 * PLANE2, &mapBl, kb * TK2, row_b, full(stage));
+          if (++stage == NSTAGE2) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_tf32(TM, TN);
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        mbar_wait(tempty, acc_phase ^ 1u);  // the epilogue has drained the previous tile
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full(stage), phase);
+          tc_fence_after();
+          const uint32_t s0 = base + stage * STAGE2_BYTES;
+          const uint64_t b_hi = umma_desc_sw64(s0 + 2 * PLANE2), b_lo = umma_desc_sw64(s0 + 3 * PLANE2);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t a_hi = umma_desc_sw64(s0 + h * (PLANE2 / 2)), a_lo = umma_desc_sw64(s0 + PLANE2 + h * (PLANE2 / 2));
+            const uint32_t d_tmem = tmem_base + (uint32_t)(h * TN);
+#pragma unroll
+            for (int k8 = 0; k8 < TK2 / UK; ++k8) {
+              const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);
+              tc_mma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | k8) != 0);
+              tc_mma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+              tc_mma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+            }
+          }
+          tc_commit(empty(stage));
+          if (++stage == NSTAGE2) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull);
+        acc_phase ^= 1u;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int64_t tm, tn;
+      tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+      mbar_wait(tfull, acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int64_t row = tm * TM2 + h * TM + q * 32 + lane;
+        float* crow = p.C + row;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (uint32_t)(h * TN + c0) + ((uint32_t)(q * 32) << 16), r);
+          const int64_t col0 = tn * TN + c0;
+          if (row < p.m) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int64_t col = col0 + j;
+              if (col < p.n) {
+                float v = p.alpha * __uint_as_float(r[j]);
+                float* pc = crow + col * p.ldc;
+                if (!p.beta_zero) v = fmaf(p.beta, *pc, v);
+                *pc = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty);
+      acc_phase ^= 1u;
     }
   }
   tc_fence_before();
@@ -555,15 +712,16 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 // K-major panel: rows x K floats, row pitch Kp floats; box = 32 floats (128 bytes) x box_rows, SWIZZLE_128B
-int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t Kp, int box_rows) {
+int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t Kp, int box_rows, int box_k = TK) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)Kp * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, box_k == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
 }
@@ -662,6 +820,31 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     count_launch();
   }
   B200_CUDA_TRY(cudaGetLastError());
+  static const int force_tile = [] { const char* e = getenv("B200BLAS_TF32_TILE"); return e ? atoi(e) : 0; }();
+  const bool big = force_tile ? force_tile == 256 : (p.k >= 2048 && p.m >= 1024 && p.n >= 1024);
+  if (big) {
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (make_map(&mAh, Ah, p.m, p.k, Kp, 256, TK2) || make_map(&mAl, Al, p.m, p.k, Kp, 256, TK2) ||
+        make_map(&mBh, Bh, p.n, p.k, Kp, 256, TK2) || make_map(&mBl, Bl, p.n, p.k, Kp, 256, TK2))
+      return (int)cudaErrorInvalidValue;
+    Tf32Params prm;
+    prm.m = p.m; prm.n = p.n; prm.k = p.k;
+    prm.C = (float*)p.C; prm.ldc = p.ldc;
+    prm.alpha = (float)p.alpha[0]; prm.beta = (float)p.beta[0];
+    prm.beta_zero = (p.beta[0] == 0.0);
+    prm.tiles_m = (p.m + TM2 - 1) / TM2; prm.tiles_n = (p.n + TN - 1) / TN;
+    static bool attr2_done = false;
+    if (!attr2_done) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      attr2_done = true;
+    }
+    const int64_t nt = prm.tiles_m * prm.tiles_n;
+    const unsigned g2 = (unsigned)(nt < sm_count() ? nt : sm_count());
+    note_variant("tf32x3_tcgen05_256x256x16");
+    tf32x3_gemm256_kernel<<<g2, THREADS, SMEM2_BYTES, s>>>(mAh, mAl, mBh, mBl, prm);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   CUtensorMap mAh, mAl, mBh, mBl;
   if (make_map(&mAh, Ah, p.m, p.k, Kp, TM) || make_map(&mAl, Al, p.m, p.k, Kp, TM) ||
       make_map(&mBh, Bh, p.n, p.k, Kp, TN) || make_map(&mBl, Bl, p.n, p.k, Kp, TN))

@@ -79,6 +79,7 @@ class DistGemm:
         self.r0, self.r1, self.c0, self.c1 = self.tiles[self.rank]
         self.mi, self.nj = self.r1 - self.r0, self.c1 - self.c0
         self.chunks = chunk_ranges(k, kchunks)
+        self.nsub = max(1, subslabs)
         self.sub = [(a + self.c0, b + self.c0) for a, b in split(self.nj, max(1, subslabs), 128) if b > a]
         self.dtype = {"s": torch.float32, "d": torch.float64, "c": torch.complex64, "z": torch.complex128}[t]
         self.backend = dist.get_backend()
@@ -107,8 +108,8 @@ class DistGemm:
         if is_root:
             self.recv = {r: torch.empty(tl[3] - tl[2], tl[1] - tl[0], **kw) for r, tl in enumerate(self.tiles) if r != 0}
         if self.dev.type == "cuda":
-            self.comm = torch.cuda.Stream()
-            self.out = torch.cuda.Stream()
+            self.comm = torch.cuda.Stream(priority=-1)   # panel traffic outranks the GEMM CTAs already queued
+            self.out = torch.cuda.Stream(priority=-1)
         else:
             self.comm = self.out = None
 
@@ -150,7 +151,15 @@ class DistGemm:
                     else:
                         buf = self.Ai[k0:k1]
                     dist.broadcast(buf, src=leader, group=self.row_groups[i])
-        # ---- B column panels: Bt[c0:c1, k0:k1] ----
+        # ---- B column panels: Bt[c0:c1, k0:k1]; the root's sends of one chunk go out as ONE grouped NCCL launch ----
+        p2p, mine = [], None
+
+        def flush():
+            if p2p:
+                for req in dist.batch_isend_irecv(p2p):
+                    req.wait()
+                del p2p[:]
+
         for j in range(self.pc):
             leader = j
             cols = split(self.n, self.pc, 128)[j]
@@ -162,14 +171,19 @@ class DistGemm:
                 dist.broadcast(buf, src=0)
             else:
                 if self.rank == 0 and leader != 0:
-                    dist.send(B[cols[0]:cols[1], k0:k1].contiguous(), dst=leader)
+                    p2p.append(dist.P2POp(dist.isend, B[cols[0]:cols[1], k0:k1].contiguous(), leader))
                 elif self.rank == leader and leader != 0:
-                    dist.recv(stage, src=0)
+                    p2p.append(dist.P2POp(dist.irecv, stage, 0))
+                if self.pr > 1:
+                    flush()
                 if self.j == j and self.pr > 1:
                     buf = B[cols[0]:cols[1], k0:k1].contiguous() if self.rank == 0 else stage
                     dist.broadcast(buf, src=leader, group=self.col_groups[j])
             if stage is not None:
-                self.Bj[:, k0:k1].copy_(stage)   # strided device copy on the comm stream
+                mine = stage
+        flush()
+        if mine is not None:
+            self.Bj[:, k0:k1].copy_(mine)   # strided device copy on the comm stream
 
     def _local(self, A, B, C, cols, ks, first):
         """One local product on this rank's tile: columns `cols` (global), k range `ks`."""
@@ -194,54 +208,70 @@ class DistGemm:
 
     # -- the product ----------------------------------------------------------------------------------------------
     def run(self, A=None, B=None, C=None):
-        """A: (k, m), B: (n, k), C: (n, m) torch tensors on rank 0 (None elsewhere).  C is updated in place."""
+        """A: (k, m), B: (n, k), C: (n, m) torch tensors on rank 0 (None elsewhere).  C is updated in place.
+
+        Schedule: k-chunks of the panels stream over NVLink on the comm stream while the compute stream applies every
+        chunk that has landed to the whole local tile (beta only on the first chunk).  The LAST chunk is applied
+        sub-slab by sub-slab, and each finished column sub-slab goes back to the root on the out stream while the
+        next one computes; the root folds beta*C in as the tiles arrive."""
         torch, dist = self.torch, self.dist
         cur = torch.cuda.current_stream() if self.dev.type == "cuda" else None
         start = self._event(cur)
         self._wait(self.comm, start)
         self._wait(self.out, start)
         ready = []
-        # phase 1: stream k chunks; first sub-slab accumulates as chunks land
         for ci in range(len(self.chunks)):
             with self._on(self.comm):
                 self._distribute_chunk(A, B, ci)
                 ready.append(self._event(self.comm))
+        last = len(self.chunks) - 1
+        whole = (self.c0, self.c1)
+        sends = []
         for ci, ks in enumerate(self.chunks):
             self._wait(cur, ready[ci])
-            if self.sub:
-                self._local(A, B, C, self.sub[0], ks, ci == 0)
-        sends = []
-        if self.sub:
-            sends.append((0, self._event(cur)))
-        # phase 2: remaining sub-slabs, full k
-        for si in range(1, len(self.sub)):
-            self._local(A, B, C, self.sub[si], (0, self.k), True)
-            sends.append((si, self._event(cur)))
-        # gather: every finished sub-slab goes to the root on the out stream while the next one computes
+            if not self.sub:
+                continue
+            if ci < last:
+                self._local(A, B, C, whole, ks, ci == 0)
+            else:
+                for si, cols in enumerate(self.sub):
+                    self._local(A, B, C, cols, ks, ci == 0)
+                    sends.append((si, self._event(cur)))
         with self._on(self.out):
-            for si, ev in sends:
-                self._wait(self.out, ev)
-                if self.rank != 0:
-                    c0, c1 = self.sub[si]
-                    dist.send(self.P[c0 - self.c0:c1 - self.c0], dst=0)
-                else:
-                    for r, tl in enumerate(self.tiles):
-                        if r == 0:
-                            continue
-                        subs = [(a + tl[2], b + tl[2]) for a, b in split(tl[3] - tl[2], max(1, len(self.sub)), 128) if b > a]
-                        if si >= len(subs):
-                            continue
-                        s0, s1 = subs[si]
-                        buf = self.recv[r][s0 - tl[2]:s1 - tl[2]]
-                        dist.recv(buf, src=r)
-                        dst = C[s0:s1, tl[0]:tl[1]]
-                        if self.beta == 0:
-                            dst.copy_(buf)
-                        else:
-                            if self.beta != 1:
-                                dst.mul_(self.beta)
-                            dst.add_(buf)
+            for si in range(self.nsub):
+                if si < len(sends):
+                    self._wait(self.out, sends[si][1])
+                self._gather_subslab(C, si)
             fin = self._event(self.out)
         self._wait(cur, fin)
         if self.comm is not None:
             cur.wait_stream(self.comm)
+
+    def _gather_subslab(self, C, si):
+        dist = self.dist
+        ops, folds = [], []
+        if self.rank != 0:
+            if si < len(self.sub):
+                c0, c1 = self.sub[si]
+                ops.append(dist.P2POp(dist.isend, self.P[c0 - self.c0:c1 - self.c0], 0))
+        else:
+            for r, tl in enumerate(self.tiles):
+                if r == 0:
+                    continue
+                subs = [(a + tl[2], b + tl[2]) for a, b in split(tl[3] - tl[2], max(1, self.nsub), 128) if b > a]
+                if si >= len(subs) or tl[1] <= tl[0]:
+                    continue
+                s0, s1 = subs[si]
+                buf = self.recv[r][s0 - tl[2]:s1 - tl[2]]
+                ops.append(dist.P2POp(dist.irecv, buf, r))
+                folds.append((buf, C[s0:s1, tl[0]:tl[1]]))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for buf, dst in folds:
+            if self.beta == 0:
+                dst.copy_(buf)
+            else:
+                if self.beta != 1:
+                    dst.mul_(self.beta)
+                dst.add_(buf)

@@ -11,7 +11,8 @@ from eigen_b200 import parallelize  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 shapes = [("d", 3000, 2500, 4100, 0.7, 1.3), ("d", 8192, 8192, 8192, 1.0, 1.0), ("s", 4096, 4096, 4096, 1.0, 1.0),
           ("z", 2048, 2048, 2048, 1.0, 1.0)]
 for (t, m, n, k, alpha, beta) in shapes:
