@@ -821,7 +821,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
   }
   B200_CUDA_TRY(cudaGetLastError());
   static const int force_tile = [] { const char* e = getenv("B200BLAS_TF32_TILE"); return e ? atoi(e) : 0; }();
-  const bool big = force_tile ? force_tile == 256 : (p.k >= 2048 && p.m >= 1024 && p.n >= 1024);
+  const bool big = force_tile == 256;  // measured slower than the 128x256 kernel (profiles/variant_sweep_r01.md): opt-in only
   if (big) {
     CUtensorMap mAh, mAl, mBh, mBl;
     if (make_map(&mAh, Ah, p.m, p.k, Kp, 256, TK2) || make_map(&mAl, Al, p.m, p.k, Kp, 256, TK2) ||

@@ -275,3 +275,77 @@ class DistGemm:
                 if self.beta != 1:
                     dst.mul_(self.beta)
                 dst.add_(buf)
+
+    # -- host-origin product (operands in shared, pinned host memory) ---------------------------------------------
+    def run_host(self, hA, hB, hC):
+        """End-to-end variant: A (k, m), B (n, k), C (n, m) are CPU tensors that every rank can address (POSIX shared
+        memory mapped and cudaHostRegister'ed by each process).  Each GPU pulls only its share over its OWN PCIe link:
+        1/N of A (k-block `rank`, then NCCL all-gather over NVLink), its column panel B_j and tile C_j, multiplies,
+        and writes C_j straight back into the caller's matrix -- no funnel through GPU 0.  Column-slab grid only."""
+        torch, dist = self.torch, self.dist
+        assert self.pr == 1, "run_host uses the 1 x N column-slab grid"
+        if self.nj <= 0:
+            dist.barrier()
+            return
+        cur = torch.cuda.current_stream()
+        kw = dict(dtype=self.dtype, device=self.dev)
+        if not hasattr(self, "hA_full"):
+            self.hA_full = torch.empty(self.k, self.m, **kw)
+            self.hB_j = torch.empty(self.nj, self.k, **kw)
+            self.hC_j = torch.empty(self.nj, self.m, **kw)
+        start = self._event(cur)
+        self._wait(self.comm, start)
+        self._wait(self.out, start)
+        even = self.k % self.world == 0
+        with self._on(self.comm):
+            if even:
+                kb = self.k // self.world
+                mine = self.hA_full[self.rank * kb:(self.rank + 1) * kb]
+                mine.copy_(hA[self.rank * kb:(self.rank + 1) * kb], non_blocking=True)
+                dist.all_gather_into_tensor(self.hA_full, mine)
+            else:
+                self.hA_full.copy_(hA, non_blocking=True)
+            a_ready = self._event(self.comm)
+        # B_j / C_j ride on the compute stream's copy engine queue while A is gathered
+        self.hB_j.copy_(hB[self.c0:self.c1], non_blocking=True)
+        if self.beta != 0:
+            self.hC_j.copy_(hC[self.c0:self.c1], non_blocking=True)
+        self._wait(cur, a_ready)
+        evs = []
+        for (s0, s1) in self.sub:
+            self.gemm(self.t, "N", "N", self.m, s1 - s0, self.k, self.alpha, self.hA_full, self.m,
+                      self.hB_j[s0 - self.c0:s1 - self.c0], self.k, self.beta, self.hC_j[s0 - self.c0:s1 - self.c0], self.m)
+            evs.append(self._event(cur))
+        with self._on(self.out):
+            for (s0, s1), ev in zip(self.sub, evs):
+                self._wait(self.out, ev)
+                hC[s0:s1].copy_(self.hC_j[s0 - self.c0:s1 - self.c0], non_blocking=True)
+            fin = self._event(self.out)
+        self._wait(cur, fin)
+        cur.wait_stream(self.comm)
+        self.h2d_bytes = (self.k // self.world if even else self.k) * self.m * hA.element_size() + \
+            self.nj * self.k * hB.element_size() + (self.nj * self.m * hC.element_size() if self.beta != 0 else 0)
+        self.d2h_bytes = self.nj * self.m * hC.element_size()
+
+
+def shared_host_tensor(name, shape, dtype, create):
+    """A CPU tensor backed by POSIX shared memory (/dev/shm/<name>), mapped by every rank and page-locked for CUDA in
+    the calling process.  `create` = True on the rank that owns the data."""
+    import torch
+    numel = 1
+    for d in shape:
+        numel *= d
+    path = "/dev/shm/" + name
+    if create and os.path.exists(path):
+        os.unlink(path)
+    t = torch.from_file(path, shared=True, size=numel, dtype=dtype)
+    return t.view(*shape)
+
+
+def pin_host_range(t):
+    """cudaHostRegister the memory of a (contiguous) CPU tensor view in this process."""
+    import torch
+    rt = torch.cuda.cudart()
+    err = rt.cudaHostRegister(t.data_ptr(), t.numel() * t.element_size(), 0)
+    if int(err) != 0:
+        raise RuntimeError("cudaHostRegister failed: %s" % (err,))
