@@ -61,13 +61,34 @@ def partition(m, n, world, grid=None, quantum=128):
 
 
 def chunk_ranges(k, nchunks, quantum=256):
+    """Equal k-chunks (nchunks > 0), or -- nchunks == 0 -- the geometric schedule k/16, k/4, k: the first chunk is small
+    so that compute starts after ~1/16 of the panel traffic, the later ones are large so that per-launch overheads
+    (pipeline fill, C read-modify-write, wave tails) stay negligible; NVLink delivers panels ~5x faster than the DMMA
+    pipe consumes them, so every later chunk has landed before it is needed."""
+    if nchunks == 0:
+        if k < 16 * quantum:
+            return [(0, k)]
+        b1 = max(quantum, (k // 16) // quantum * quantum)
+        b2 = max(b1 + quantum, (k // 4) // quantum * quantum)
+        return [(0, b1), (b1, b2), (b2, k)]
     return [r for r in split(k, max(1, nchunks), quantum) if r[1] > r[0]]
+
+
+def subslab_ranges(width, nsub, quantum=128):
+    """Column sub-slabs of a tile for the gather pipeline.  nsub == 0: a large first part and a small last part
+    (3/4 + 1/4), so that only a quarter of the tile is still on the wire when the last product finishes."""
+    if nsub == 0:
+        if width < 8 * quantum:
+            return [(0, width)] if width > 0 else []
+        cut = (width * 3 // 4) // quantum * quantum
+        return [(0, cut), (cut, width)]
+    return [r for r in split(width, max(1, nsub), quantum) if r[1] > r[0]]
 
 
 class DistGemm:
     """C = alpha*A*B + beta*C across all ranks of the default process group (operands root-resident)."""
 
-    def __init__(self, t, m, n, k, alpha, beta, kchunks=8, subslabs=4, grid=None):
+    def __init__(self, t, m, n, k, alpha, beta, kchunks=0, subslabs=0, grid=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
@@ -79,8 +100,9 @@ class DistGemm:
         self.r0, self.r1, self.c0, self.c1 = self.tiles[self.rank]
         self.mi, self.nj = self.r1 - self.r0, self.c1 - self.c0
         self.chunks = chunk_ranges(k, kchunks)
-        self.nsub = max(1, subslabs)
-        self.sub = [(a + self.c0, b + self.c0) for a, b in split(self.nj, max(1, subslabs), 128) if b > a]
+        self.nsub_arg = subslabs
+        self.sub = [(a + self.c0, b + self.c0) for a, b in subslab_ranges(self.nj, subslabs)]
+        self.nsub = max(len(subslab_ranges(tl[3] - tl[2], subslabs)) for tl in self.tiles)
         self.dtype = {"s": torch.float32, "d": torch.float64, "c": torch.complex64, "z": torch.complex128}[t]
         self.backend = dist.get_backend()
         self.dev = torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu")
@@ -258,7 +280,7 @@ class DistGemm:
             for r, tl in enumerate(self.tiles):
                 if r == 0:
                     continue
-                subs = [(a + tl[2], b + tl[2]) for a, b in split(tl[3] - tl[2], max(1, self.nsub), 128) if b > a]
+                subs = [(a + tl[2], b + tl[2]) for a, b in subslab_ranges(tl[3] - tl[2], self.nsub_arg)]
                 if si >= len(subs) or tl[1] <= tl[0]:
                     continue
                 s0, s1 = subs[si]
@@ -306,23 +328,31 @@ class DistGemm:
             else:
                 self.hA_full.copy_(hA, non_blocking=True)
             a_ready = self._event(self.comm)
-        # B_j / C_j ride on the compute stream's copy engine queue while A is gathered
-        self.hB_j.copy_(hB[self.c0:self.c1], non_blocking=True)
-        if self.beta != 0:
-            self.hC_j.copy_(hC[self.c0:self.c1], non_blocking=True)
+        # B_j / C_j sub-slabs are uploaded on the out stream's copy queue in the order they are consumed, so that the
+        # upload of sub-slab s+1 overlaps the product on sub-slab s
+        hsub = [(a + self.c0, b + self.c0) for a, b in split(self.nj, 4, 128) if b > a]
+        up = []
+        with self._on(self.out):
+            for (s0, s1) in hsub:
+                self.hB_j[s0 - self.c0:s1 - self.c0].copy_(hB[s0:s1], non_blocking=True)
+                if self.beta != 0:
+                    self.hC_j[s0 - self.c0:s1 - self.c0].copy_(hC[s0:s1], non_blocking=True)
+                up.append(self._event(self.out))
         self._wait(cur, a_ready)
         evs = []
-        for (s0, s1) in self.sub:
+        for (s0, s1), u in zip(hsub, up):
+            self._wait(cur, u)
             self.gemm(self.t, "N", "N", self.m, s1 - s0, self.k, self.alpha, self.hA_full, self.m,
                       self.hB_j[s0 - self.c0:s1 - self.c0], self.k, self.beta, self.hC_j[s0 - self.c0:s1 - self.c0], self.m)
             evs.append(self._event(cur))
-        with self._on(self.out):
-            for (s0, s1), ev in zip(self.sub, evs):
-                self._wait(self.out, ev)
+        with self._on(self.comm):   # downloads use the other copy queue (D2H engine), behind the A gather
+            for (s0, s1), ev in zip(hsub, evs):
+                self._wait(self.comm, ev)
                 hC[s0:s1].copy_(self.hC_j[s0 - self.c0:s1 - self.c0], non_blocking=True)
-            fin = self._event(self.out)
+            fin = self._event(self.comm)
         self._wait(cur, fin)
         cur.wait_stream(self.comm)
+        cur.wait_stream(self.out)
         self.h2d_bytes = (self.k // self.world if even else self.k) * self.m * hA.element_size() + \
             self.nj * self.k * hB.element_size() + (self.nj * self.m * hC.element_size() if self.beta != 0 else 0)
         self.d2h_bytes = self.nj * self.m * hC.element_size()

@@ -28,6 +28,10 @@ def test_split_and_partition_follow_parallelize_gemm_rules():
         cover[r0:r1, c0:c1] += 1
     assert np.all(cover == 1)
     assert parallelize.chunk_ranges(1000, 3) == [(0, 512), (512, 1000)]
+    assert parallelize.chunk_ranges(16384, 0) == [(0, 1024), (1024, 4096), (4096, 16384)]
+    assert parallelize.chunk_ranges(1000, 0) == [(0, 1000)]
+    assert parallelize.subslab_ranges(2048, 0) == [(0, 1536), (1536, 2048)]
+    assert parallelize.subslab_ranges(300, 0) == [(0, 300)]
     assert parallelize.grid_for(8) == (1, 8)
 
 
@@ -53,7 +57,10 @@ def _worker(rank, world, port, grid, shape, beta, out):
     import eigen_b200
     eigen_b200.gemm_dev = _cpu_gemm_stand_in   # patched in this test process only
     m, n, k = shape
-    job = parallelize.DistGemm("d", m, n, k, 0.7, beta, kchunks=3, subslabs=2, grid=grid)
+    if k > 4000:
+        job = parallelize.DistGemm("d", m, n, k, 0.7, beta, grid=grid)
+    else:
+        job = parallelize.DistGemm("d", m, n, k, 0.7, beta, kchunks=3, subslabs=2, grid=grid)
     if rank == 0:
         g = torch.Generator().manual_seed(5)
         A = torch.rand(k, m, dtype=torch.float64, generator=g) * 2 - 1
@@ -85,6 +92,7 @@ def _free_port():
     (2, (2, 1), (300, 260, 515), 0.0),
     (4, (2, 2), (390, 410, 600), 1.3),
     (4, (1, 4), (130, 1000, 300), 1.0),
+    (2, (1, 2), (140, 2300, 4200), 1.0),   # default geometric k-chunks and 3/4 + 1/4 sub-slabs
 ])
 def test_distgemm_gloo(world, grid, shape, beta):
     ctx = mp.get_context("spawn")
