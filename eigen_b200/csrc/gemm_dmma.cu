@@ -25,11 +25,9 @@
 namespace b200 {
 namespace {
 
-constexpr int BK = 16, STAGES = 4;
-
-template <int BM_, int BN_, int WM_, int WN_, int MINB_>
+template <int BM_, int BN_, int WM_, int WN_, int MINB_, int BK_ = 16, int STAGES_ = 4>
 struct Cfg {
-  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, MINB = MINB_;
+  static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, MINB = MINB_, BK = BK_, STAGES = STAGES_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int THREADS = WARPS_M * WARPS_N * 32;
   static constexpr int MI = WM / 8, NJ = WN / 8;
@@ -49,7 +47,7 @@ struct PanelSrc {
 
 // Per-thread loader state for one operand panel of PR real rows: copy e (0 <= e < E) moves `bytes` bytes from
 // p + e*estep to smem offset soff + e*sstep and belongs to k index kk0 + e*kkstep of the tile.
-template <int PR, int THREADS, bool CPLX>
+template <int PR, int THREADS, bool CPLX, int BK>
 struct Loader {
   const double* p;
   uint32_t soff;
@@ -97,14 +95,15 @@ struct Loader {
         if (e < E && dim0 + r0 + (int64_t)e * rstep < s.dim) vmask |= 1u << e;
     }
   }
-  // issue copy e of the tile whose first k index is k0 (klimit = k for the ragged last tile, else "infinite")
-  __device__ __forceinline__ void copy(double* S, const PanelSrc& s, int e, int64_t kt, int64_t k0, int64_t k) const {
-    const bool ok = ((vmask >> e) & 1u) && (k0 + kk0 + e * kkstep < k);
-    const double* src = ok ? p + (int64_t)e * estep + kt * kstep : s.base;
+  // issue copy e of one k-tile: ptile = p advanced to the tile (computed once per tile), krem = k - k0 clamped to int
+  __device__ __forceinline__ void copy(double* S, const double* fallback, int e, const double* ptile, int krem) const {
+    const bool ok = ((vmask >> e) & 1u) && (kk0 + e * kkstep < krem);
+    const double* src = ok ? ptile + (int64_t)e * estep : fallback;
     double* dst = S + soff + e * sstep;
     if (bytes == 16) cp_async_zfill<16>(dst, src, ok ? vbytes : 0);
     else cp_async_zfill<8>(dst, src, ok ? 8 : 0);
   }
+  __device__ __forceinline__ const double* tile_ptr(int64_t kt) const { return p + kt * kstep; }
 };
 
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
@@ -137,7 +136,7 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
                  EpiParams ep, int64_t tiles_m, int64_t tiles_n) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
-  double* Bs = smem + STAGES * C::PANEL_A;
+  double* Bs = smem + C::STAGES * C::PANEL_A;
   constexpr int MI = C::MI, NJ = C::NJ;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -147,8 +146,9 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
   constexpr int SC = CPLX ? 2 : 1;  // real rows/cols per scalar
   const int64_t m0 = tm * (C::BM / SC), n0 = tn * (C::BN / SC);  // tile origin in scalars
 
-  Loader<C::BM, C::THREADS, CPLX> la;
-  Loader<C::BN, C::THREADS, CPLX> lb;
+  constexpr int BK = C::BK, STAGES = C::STAGES;
+  Loader<C::BM, C::THREADS, CPLX, BK> la;
+  Loader<C::BN, C::THREADS, CPLX, BK> lb;
   la.init(a, m0, tid, C::LDA_S);
   lb.init(b, n0, tid, C::LDB_S);
 
@@ -163,9 +163,14 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
     double* sa = As + (kt % STAGES) * C::PANEL_A;
     double* sb = Bs + (kt % STAGES) * C::PANEL_B;
 #pragma unroll
-    for (int e = 0; e < 16; ++e) if (e < la.E) la.copy(sa, a, e, kt, kt * BK, k);
+    const int64_t rem = k - kt * BK;
+    const int krem = rem > (1 << 20) ? (1 << 20) : (int)rem;
+    const double* pa = la.tile_ptr(kt);
+    const double* pb = lb.tile_ptr(kt);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) if (e < lb.E) lb.copy(sb, b, e, kt, kt * BK, k);
+    for (int e = 0; e < 16; ++e) if (e < la.E) la.copy(sa, a.base, e, pa, krem);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (e < lb.E) lb.copy(sb, b.base, e, pb, krem);
   };
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -181,6 +186,10 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
     const bool do_load = nxt < nkt;
     double* sa_n = As + (nxt % STAGES) * C::PANEL_A;
     double* sb_n = Bs + (nxt % STAGES) * C::PANEL_B;
+    const int64_t rem_n = k - nxt * BK;
+    const int krem_n = rem_n > (1 << 20) ? (1 << 20) : (int)rem_n;
+    const double* pa_n = la.tile_ptr(nxt);
+    const double* pb_n = lb.tile_ptr(nxt);
     const double* As_ = As + (kt % STAGES) * C::PANEL_A + wm * C::WM + fr;
     const double* Bs_ = Bs + (kt % STAGES) * C::PANEL_B + wn * C::WN + fr;
 #pragma unroll
@@ -194,9 +203,9 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
       if (do_load) {
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          if ((e & 3) == k4) {
-            if (e < la.E) la.copy(sa_n, a, e, nxt, nxt * BK, k);
-            if (e < lb.E) lb.copy(sb_n, b, e, nxt, nxt * BK, k);
+          if ((e % (BK / 4)) == k4) {
+            if (e < la.E) la.copy(sa_n, a.base, e, pa_n, krem_n);
+            if (e < lb.E) lb.copy(sb_n, b.base, e, pb_n, krem_n);
           }
         }
       }
@@ -267,6 +276,7 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 using CfgA = Cfg<128, 128, 64, 32, 1>;  // 8 warps, 64x32 warp tiles, 1 CTA / SM
 using CfgB = Cfg<128, 64, 32, 32, 2>;   // 8 warps, 32x32 warp tiles, 2 CTAs / SM
 using CfgC = Cfg<128, 128, 32, 32, 1>;  // 16 warps, 32x32 warp tiles, 1 CTA / SM
+using CfgD = Cfg<128, 64, 32, 32, 2, 32, 2>;  // as B with BK = 32, double buffered: half as many CTA barriers
 
 template <typename C, bool CPLX>
 int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
@@ -289,7 +299,8 @@ int dmma_cfg() {
   static int cfg = [] {
     const char* e = getenv("B200BLAS_DMMA_CFG");
     if (!e) return -1;
-    return (e[0] == 'A' || e[0] == 'a') ? 0 : (e[0] == 'B' || e[0] == 'b') ? 1 : (e[0] == 'C' || e[0] == 'c') ? 2 : -1;
+    return (e[0] == 'A' || e[0] == 'a') ? 0 : (e[0] == 'B' || e[0] == 'b') ? 1 : (e[0] == 'C' || e[0] == 'c') ? 2
+           : (e[0] == 'D' || e[0] == 'd') ? 3 : -1;
   }();
   return cfg;
 }
@@ -323,12 +334,14 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
     switch (cfg) {
       case 0: note_variant("dmma_z_A_64x64x16_w32x16"); return launch_cfg<CfgA, true>(p, s, a, b, ep);
       case 2: note_variant("dmma_z_C_64x64x16_w16x16"); return launch_cfg<CfgC, true>(p, s, a, b, ep);
+      case 3: note_variant("dmma_z_D_64x32x32_w16x16_2cta"); return launch_cfg<CfgD, true>(p, s, a, b, ep);
       default: note_variant("dmma_z_B_64x32x16_w16x16_2cta"); return launch_cfg<CfgB, true>(p, s, a, b, ep);
     }
   }
   switch (cfg) {
     case 0: note_variant("dmma_d_A_128x128x16_w64x32"); return launch_cfg<CfgA, false>(p, s, a, b, ep);
     case 2: note_variant("dmma_d_C_128x128x16_w32x32"); return launch_cfg<CfgC, false>(p, s, a, b, ep);
+    case 3: note_variant("dmma_d_D_128x64x32_w32x32_2cta"); return launch_cfg<CfgD, false>(p, s, a, b, ep);
     default: note_variant("dmma_d_B_128x64x16_w32x32_2cta"); return launch_cfg<CfgB, false>(p, s, a, b, ep);
   }
 }

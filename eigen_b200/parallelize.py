@@ -61,27 +61,29 @@ def partition(m, n, world, grid=None, quantum=128):
 
 
 def chunk_ranges(k, nchunks, quantum=256):
-    """Equal k-chunks (nchunks > 0), or -- nchunks == 0 -- the geometric schedule k/16, k/4, k: the first chunk is small
-    so that compute starts after ~1/16 of the panel traffic, the later ones are large so that per-launch overheads
-    (pipeline fill, C read-modify-write, wave tails) stay negligible; NVLink delivers panels ~5x faster than the DMMA
-    pipe consumes them, so every later chunk has landed before it is needed."""
+    """Equal k-chunks (nchunks > 0), or -- nchunks == 0 -- the doubling schedule k/16, k/16, k/8, k/4, k/2.
+    Compute starts after 1/16 of the panel traffic; each later chunk is as large as everything before it, so it has
+    landed by the time it is needed whenever the links deliver panels at least twice as fast as the DMMA pipe
+    consumes them (measured at 8 GPUs: 12.5 ms of root egress against 33.5 ms of compute), and only five launches
+    pay the per-launch costs (pipeline fill, C read-modify-write, wave tails)."""
     if nchunks == 0:
         if k < 16 * quantum:
             return [(0, k)]
-        b1 = max(quantum, (k // 16) // quantum * quantum)
-        b2 = max(b1 + quantum, (k // 4) // quantum * quantum)
-        return [(0, b1), (b1, b2), (b2, k)]
+        u = max(quantum, (k // 16) // quantum * quantum)
+        cuts = [0, u, 2 * u, 4 * u, 8 * u, k]
+        return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
     return [r for r in split(k, max(1, nchunks), quantum) if r[1] > r[0]]
 
 
 def subslab_ranges(width, nsub, quantum=128):
-    """Column sub-slabs of a tile for the gather pipeline.  nsub == 0: a large first part and a small last part
-    (3/4 + 1/4), so that only a quarter of the tile is still on the wire when the last product finishes."""
+    """Column sub-slabs of a tile for the gather pipeline.  nsub == 0: 1/2 + 3/8 + 1/8, so that only an eighth of
+    the tile is still on the wire when the last product finishes."""
     if nsub == 0:
-        if width < 8 * quantum:
+        if width < 16 * quantum:
             return [(0, width)] if width > 0 else []
-        cut = (width * 3 // 4) // quantum * quantum
-        return [(0, cut), (cut, width)]
+        c1 = (width // 2) // quantum * quantum
+        c2 = (width * 7 // 8) // quantum * quantum
+        return [(0, c1), (c1, c2), (c2, width)]
     return [r for r in split(width, max(1, nsub), quantum) if r[1] > r[0]]
 
 
@@ -306,15 +308,12 @@ class DistGemm:
         and writes C_j straight back into the caller's matrix -- no funnel through GPU 0.  Column-slab grid only."""
         torch, dist = self.torch, self.dist
         assert self.pr == 1, "run_host uses the 1 x N column-slab grid"
-        if self.nj <= 0:
-            dist.barrier()
-            return
         cur = torch.cuda.current_stream()
         kw = dict(dtype=self.dtype, device=self.dev)
         if not hasattr(self, "hA_full"):
             self.hA_full = torch.empty(self.k, self.m, **kw)
-            self.hB_j = torch.empty(self.nj, self.k, **kw)
-            self.hC_j = torch.empty(self.nj, self.m, **kw)
+            self.hB_j = torch.empty(max(self.nj, 1), self.k, **kw)
+            self.hC_j = torch.empty(max(self.nj, 1), self.m, **kw)
         start = self._event(cur)
         self._wait(self.comm, start)
         self._wait(self.out, start)

@@ -28,9 +28,9 @@ def test_split_and_partition_follow_parallelize_gemm_rules():
         cover[r0:r1, c0:c1] += 1
     assert np.all(cover == 1)
     assert parallelize.chunk_ranges(1000, 3) == [(0, 512), (512, 1000)]
-    assert parallelize.chunk_ranges(16384, 0) == [(0, 1024), (1024, 4096), (4096, 16384)]
+    assert parallelize.chunk_ranges(16384, 0) == [(0, 1024), (1024, 2048), (2048, 4096), (4096, 8192), (8192, 16384)]
     assert parallelize.chunk_ranges(1000, 0) == [(0, 1000)]
-    assert parallelize.subslab_ranges(2048, 0) == [(0, 1536), (1536, 2048)]
+    assert parallelize.subslab_ranges(2048, 0) == [(0, 1024), (1024, 1792), (1792, 2048)]
     assert parallelize.subslab_ranges(300, 0) == [(0, 300)]
     assert parallelize.grid_for(8) == (1, 8)
 
@@ -92,7 +92,7 @@ def _free_port():
     (2, (2, 1), (300, 260, 515), 0.0),
     (4, (2, 2), (390, 410, 600), 1.3),
     (4, (1, 4), (130, 1000, 300), 1.0),
-    (2, (1, 2), (140, 2300, 4200), 1.0),   # default geometric k-chunks and 3/4 + 1/4 sub-slabs
+    (2, (1, 2), (140, 4300, 4200), 1.0),   # default doubling k-chunks and 1/2 + 3/8 + 1/8 sub-slabs
 ])
 def test_distgemm_gloo(world, grid, shape, beta):
     ctx = mp.get_context("spawn")
