@@ -15,9 +15,9 @@
 //     columns, P=Ar.Br, Q=Ar.Bi, R=Ai.Br, S=Ai.Bi; the epilogue combines re = P -/+ S, im = +/-Q +/- R with the four
 //     conjugation sign patterns of gebp_traits::acc (:714-738);
 //   * the epilogue fuses alpha and beta (the reference scales C by beta in a separate pass, blas/level3_impl.h:62-66).
-// Tile configurations (template Cfg): 128x128 tile / 8 warps of 64x32 / 1 CTA per SM, 128x64 tile / 8 warps of
-// 32x32 / 2 CTAs per SM, 128x128 tile / 16 warps of 32x32; the default is chosen from measurements
-// (profiles/dmma_cfg_sweep_r01.md), B200BLAS_DMMA_CFG overrides it.
+// Tile configuration: 128x64x16 CTA tile, 8 warps of 32x32, 2 CTAs per SM (chosen from the sweep in
+// profiles/variant_sweep_r01.md over 128x128/1-CTA, 128x64/2-CTA, 16-warp and BK=32 variants).  The loader mode of
+// each operand (16-byte / 8-byte / transposed) is a template parameter so that no mode state occupies registers.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -45,65 +45,68 @@ struct PanelSrc {
   int vec16;           // 1: 16-byte cp.async (alignment checked on the host); always 1 for complex
 };
 
-// Per-thread loader state for one operand panel of PR real rows: copy e (0 <= e < E) moves `bytes` bytes from
-// p + e*estep to smem offset soff + e*sstep and belongs to k index kk0 + e*kkstep of the tile.
-template <int PR, int THREADS, bool CPLX, int BK>
-struct Loader {
-  const double* p;
-  uint32_t soff;
-  int kk0;
-  uint32_t vmask;   // bit e: the row/column of copy e is inside the matrix
-  int vbytes;       // bytes actually read when valid (8 for the odd last row of a 16-byte real granule)
-  // uniform (same for all threads)
-  int64_t estep, kstep;
-  int sstep, kkstep, bytes, E;
+// Loader modes (compile time, so that no mode state lives in registers):
+//   LD_DIM16  memory contiguous along the tile dimension, 16-byte cp.async (real: 2 rows per copy; complex: 1 scalar)
+//   LD_DIM8   memory contiguous along the tile dimension, 8-byte cp.async (any alignment / odd ld; real only)
+//   LD_K      memory contiguous along k (transposed operand): 8-byte copies (real) or 16-byte scalars (complex)
+enum { LD_DIM16 = 0, LD_DIM8 = 1, LD_K = 2 };
 
-  __device__ __forceinline__ void init(const PanelSrc& s, int64_t dim0, int tid, int lds_row) {
-    const int gran = (CPLX || s.vec16) ? 2 : 1;        // doubles per copy
-    const int rs = CPLX ? 2 : 1;                        // doubles per scalar
-    const int GD = PR / gran;                           // granules along the tile dimension
-    bytes = 8 * gran;
-    E = GD * BK / THREADS;
-    vmask = 0;
-    vbytes = bytes;
-    if (s.dim_contig) {
+// Per-thread loader for one operand panel of PR real rows: copy e (0 <= e < E) moves BYTES bytes from
+// p + e*estep (+ tile offset) to smem offset soff + e*SSTEP and belongs to k index kk0 + e*KKSTEP of the tile.
+template <int PR, int THREADS, bool CPLX, int BK, int MODE, int LDS_ROW>
+struct Loader {
+  static constexpr int GRAN = (CPLX || MODE == LD_DIM16) ? 2 : 1;   // doubles per copy
+  static constexpr int RS = CPLX ? 2 : 1;                             // doubles per scalar
+  static constexpr int GD = PR / GRAN;                                // granules along the tile dimension
+  static constexpr int BYTES = 8 * GRAN;
+  static constexpr int E = GD * BK / THREADS;
+  static constexpr bool DIMC = (MODE != LD_K);
+  static constexpr int KKSTEP = DIMC ? THREADS / GD : 0;
+  static constexpr int RSTEP = THREADS / BK;                          // LD_K: scalars between consecutive copies
+  static constexpr int SSTEP = DIMC ? KKSTEP * LDS_ROW : RSTEP * RS;
+  static_assert(E >= 1 && E <= 16, "copies per thread");
+  static_assert(DIMC ? (THREADS % GD == 0) : (THREADS % BK == 0), "thread map");
+  static_assert(!(CPLX && MODE == LD_DIM8), "complex scalars move as 16-byte copies");
+
+  const double* p;   // source of copy 0 of k-tile 0
+  uint32_t soff;     // smem offset (doubles) of copy 0
+  uint32_t vmask;    // LD_K: bit e = row/column of copy e inside the matrix; DIM modes: bytes valid (0, 8, 16)
+  int kk0;           // k index of copy 0 inside the tile
+
+  __device__ __forceinline__ void init(const PanelSrc& s, int64_t dim0, int tid) {
+    if constexpr (DIMC) {
       const int rg = tid % GD;
       kk0 = tid / GD;
-      kkstep = THREADS / GD;
-      const int64_t gd = dim0 + (int64_t)rg * gran / rs;  // scalar index along the tile dimension
-      p = s.base + rs * gd + (int64_t)kk0 * s.ld * rs;
-      estep = (int64_t)kkstep * s.ld * rs;
-      kstep = (int64_t)BK * s.ld * rs;
-      soff = (uint32_t)(kk0 * lds_row + rg * gran);
-      sstep = kkstep * lds_row;
-      if (gd < s.dim) {  // gd = first scalar of the granule
-        vmask = 0xffffffffu;
-        if (!CPLX && gran == 2 && gd + 1 >= s.dim) vbytes = 8;
-      }
+      const int64_t gd = dim0 + (int64_t)rg * GRAN / RS;   // first scalar of the granule
+      p = s.base + RS * gd + (int64_t)kk0 * s.ld * RS;
+      soff = (uint32_t)(kk0 * LDS_ROW + rg * GRAN);
+      vmask = 0;
+      if (gd < s.dim) vmask = (!CPLX && GRAN == 2 && gd + 1 >= s.dim) ? 8u : (uint32_t)BYTES;
     } else {
       kk0 = tid % BK;
-      kkstep = 0;
-      const int r0 = tid / BK;                          // scalar index inside the tile for e = 0
-      const int rstep = THREADS / BK;
-      p = s.base + rs * ((int64_t)kk0 + (dim0 + r0) * s.ld);
-      estep = (int64_t)rstep * s.ld * rs;
-      kstep = (int64_t)BK * rs;
-      soff = (uint32_t)(kk0 * lds_row + r0 * rs);
-      sstep = rstep * rs;
+      const int r0 = tid / BK;
+      p = s.base + RS * ((int64_t)kk0 + (dim0 + r0) * s.ld);
+      soff = (uint32_t)(kk0 * LDS_ROW + r0 * RS);
+      vmask = 0;
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (e < E && dim0 + r0 + (int64_t)e * rstep < s.dim) vmask |= 1u << e;
+      for (int e = 0; e < E; ++e)
+        if (dim0 + r0 + (int64_t)e * RSTEP < s.dim) vmask |= 1u << e;
     }
   }
-  // issue copy e of one k-tile: ptile = p advanced to the tile (computed once per tile), krem = k - k0 clamped to int
-  __device__ __forceinline__ void copy(double* S, const double* fallback, int e, const double* ptile, int krem) const {
-    const bool ok = ((vmask >> e) & 1u) && (kk0 + e * kkstep < krem);
-    const double* src = ok ? ptile + (int64_t)e * estep : fallback;
-    double* dst = S + soff + e * sstep;
-    if (bytes == 16) cp_async_zfill<16>(dst, src, ok ? vbytes : 0);
-    else cp_async_zfill<8>(dst, src, ok ? 8 : 0);
+  __device__ __forceinline__ int64_t estep(const PanelSrc& s) const {
+    return DIMC ? (int64_t)KKSTEP * s.ld * RS : (int64_t)RSTEP * s.ld * RS;
   }
-  __device__ __forceinline__ const double* tile_ptr(int64_t kt) const { return p + kt * kstep; }
+  __device__ __forceinline__ const double* tile_ptr(const PanelSrc& s, int64_t kt) const {
+    return p + kt * (DIMC ? (int64_t)BK * s.ld * RS : (int64_t)BK * RS);
+  }
+  // issue copy e of one k-tile: ptile = tile_ptr(kt), krem = k - k0 clamped to int (ragged last tile)
+  __device__ __forceinline__ void copy(double* S, const PanelSrc& s, int e, const double* ptile, int krem) const {
+    int nbytes;
+    if constexpr (DIMC) nbytes = (kk0 + e * KKSTEP < krem) ? (int)vmask : 0;
+    else nbytes = (((vmask >> e) & 1u) && kk0 < krem) ? BYTES : 0;
+    const double* src = nbytes ? ptile + (int64_t)e * estep(s) : s.base;
+    cp_async_zfill<BYTES>(S + soff + e * SSTEP, src, nbytes);
+  }
 };
 
 __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
@@ -130,7 +133,7 @@ __device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t ti
   tn = in / gsz;
 }
 
-template <typename C, bool CPLX>
+template <typename C, bool CPLX, int AMODE, int BMODE>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double* __restrict__ Cmat, int64_t ldc,
                  EpiParams ep, int64_t tiles_m, int64_t tiles_n) {
@@ -147,10 +150,12 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
   const int64_t m0 = tm * (C::BM / SC), n0 = tn * (C::BN / SC);  // tile origin in scalars
 
   constexpr int BK = C::BK, STAGES = C::STAGES;
-  Loader<C::BM, C::THREADS, CPLX, BK> la;
-  Loader<C::BN, C::THREADS, CPLX, BK> lb;
-  la.init(a, m0, tid, C::LDA_S);
-  lb.init(b, n0, tid, C::LDB_S);
+  using LA = Loader<C::BM, C::THREADS, CPLX, BK, AMODE, C::LDA_S>;
+  using LB = Loader<C::BN, C::THREADS, CPLX, BK, BMODE, C::LDB_S>;
+  LA la;
+  LB lb;
+  la.init(a, m0, tid);
+  lb.init(b, n0, tid);
 
   double acc[MI][NJ][2];
 #pragma unroll
@@ -165,12 +170,12 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
     const int64_t rem = k - kt * BK;
     const int krem = rem > (1 << 20) ? (1 << 20) : (int)rem;
-    const double* pa = la.tile_ptr(kt);
-    const double* pb = lb.tile_ptr(kt);
+    const double* pa = la.tile_ptr(a, kt);
+    const double* pb = lb.tile_ptr(b, kt);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) if (e < la.E) la.copy(sa, a.base, e, pa, krem);
+    for (int e = 0; e < LA::E; ++e) la.copy(sa, a, e, pa, krem);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) if (e < lb.E) lb.copy(sb, b.base, e, pb, krem);
+    for (int e = 0; e < LB::E; ++e) lb.copy(sb, b, e, pb, krem);
   };
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -188,8 +193,8 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
     double* sb_n = Bs + (nxt % STAGES) * C::PANEL_B;
     const int64_t rem_n = k - nxt * BK;
     const int krem_n = rem_n > (1 << 20) ? (1 << 20) : (int)rem_n;
-    const double* pa_n = la.tile_ptr(nxt);
-    const double* pb_n = lb.tile_ptr(nxt);
+    const double* pa_n = la.tile_ptr(a, nxt);
+    const double* pb_n = lb.tile_ptr(b, nxt);
     const double* As_ = As + (kt % STAGES) * C::PANEL_A + wm * C::WM + fr;
     const double* Bs_ = Bs + (kt % STAGES) * C::PANEL_B + wn * C::WN + fr;
 #pragma unroll
@@ -204,8 +209,8 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
           if ((e % (BK / 4)) == k4) {
-            if (e < la.E) la.copy(sa_n, a.base, e, pa_n, krem_n);
-            if (e < lb.E) lb.copy(sb_n, b.base, e, pb_n, krem_n);
+            if (e < LA::E) la.copy(sa_n, a, e, pa_n, krem_n);
+            if (e < LB::E) lb.copy(sb_n, b, e, pb_n, krem_n);
           }
         }
       }
@@ -273,12 +278,11 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 
 bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
-using CfgA = Cfg<128, 128, 64, 32, 1>;  // 8 warps, 64x32 warp tiles, 1 CTA / SM
-using CfgB = Cfg<128, 64, 32, 32, 2>;   // 8 warps, 32x32 warp tiles, 2 CTAs / SM
-using CfgC = Cfg<128, 128, 32, 32, 1>;  // 16 warps, 32x32 warp tiles, 1 CTA / SM
-using CfgD = Cfg<128, 64, 32, 32, 2, 32, 2>;  // as B with BK = 32, double buffered: half as many CTA barriers
+// 128x64x16 tile, 8 warps of 32x32, 4-stage ring, 2 CTAs / SM: the two co-resident CTAs cover each other's barrier,
+// prologue and epilogue bubbles (profiles/variant_sweep_r01.md: wins or ties against 128x128 / 1 CTA per SM).
+using CfgB = Cfg<128, 64, 32, 32, 2, 16, 4>;
 
-template <typename C, bool CPLX>
+template <typename C, bool CPLX, int AMODE, int BMODE>
 int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
   const int sc = CPLX ? 2 : 1;
   const int64_t tiles_m = (p.m * sc + C::BM - 1) / C::BM, tiles_n = (p.n * sc + C::BN - 1) / C::BN;
@@ -286,23 +290,26 @@ int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const Pa
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
   static bool attr_done = false;
   if (!attr_done) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(dmma_gemm_kernel<C, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    B200_CUDA_TRY(cudaFuncSetAttribute(dmma_gemm_kernel<C, CPLX, AMODE, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  dmma_gemm_kernel<C, CPLX><<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep,
-                                                                             tiles_m, tiles_n);
+  dmma_gemm_kernel<C, CPLX, AMODE, BMODE><<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(
+      a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep, tiles_m, tiles_n);
   count_launch();
   return (int)cudaGetLastError();
 }
 
-int dmma_cfg() {
-  static int cfg = [] {
-    const char* e = getenv("B200BLAS_DMMA_CFG");
-    if (!e) return -1;
-    return (e[0] == 'A' || e[0] == 'a') ? 0 : (e[0] == 'B' || e[0] == 'b') ? 1 : (e[0] == 'C' || e[0] == 'c') ? 2
-           : (e[0] == 'D' || e[0] == 'd') ? 3 : -1;
-  }();
-  return cfg;
+template <bool CPLX, int AMODE>
+int launch_b(int bmode, const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
+  if constexpr (CPLX) {
+    return bmode == LD_K ? launch_cfg<CfgB, true, AMODE, LD_K>(p, s, a, b, ep) : launch_cfg<CfgB, true, AMODE, LD_DIM16>(p, s, a, b, ep);
+  } else {
+    switch (bmode) {
+      case LD_DIM16: return launch_cfg<CfgB, false, AMODE, LD_DIM16>(p, s, a, b, ep);
+      case LD_DIM8: return launch_cfg<CfgB, false, AMODE, LD_DIM8>(p, s, a, b, ep);
+      default: return launch_cfg<CfgB, false, AMODE, LD_K>(p, s, a, b, ep);
+    }
+  }
 }
 
 }  // namespace
@@ -328,21 +335,18 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
   ep.beta[0] = p.beta[0]; ep.beta[1] = p.beta[1];
   ep.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
   ep.conja = (p.opa == OP_C); ep.conjb = (p.opb == OP_C);
-  int cfg = dmma_cfg();
-  if (cfg < 0) cfg = 1;  // default: 128x64 tiles, 2 CTAs / SM (profiles/dmma_cfg_sweep_r01.md)
+  // loader modes: 16-byte copies need the tile dimension contiguous, a 16-byte aligned base and (real) an even ld
+  const int amode = !a.dim_contig ? LD_K : (a.vec16 ? LD_DIM16 : LD_DIM8);
+  const int bmode = !b.dim_contig ? LD_K : (b.vec16 ? LD_DIM16 : LD_DIM8);
   if (cplx) {
-    switch (cfg) {
-      case 0: note_variant("dmma_z_A_64x64x16_w32x16"); return launch_cfg<CfgA, true>(p, s, a, b, ep);
-      case 2: note_variant("dmma_z_C_64x64x16_w16x16"); return launch_cfg<CfgC, true>(p, s, a, b, ep);
-      case 3: note_variant("dmma_z_D_64x32x32_w16x16_2cta"); return launch_cfg<CfgD, true>(p, s, a, b, ep);
-      default: note_variant("dmma_z_B_64x32x16_w16x16_2cta"); return launch_cfg<CfgB, true>(p, s, a, b, ep);
-    }
+    note_variant("dmma_z_64x32x16_w16x16_2cta");
+    return amode == LD_K ? launch_b<true, LD_K>(bmode, p, s, a, b, ep) : launch_b<true, LD_DIM16>(bmode, p, s, a, b, ep);
   }
-  switch (cfg) {
-    case 0: note_variant("dmma_d_A_128x128x16_w64x32"); return launch_cfg<CfgA, false>(p, s, a, b, ep);
-    case 2: note_variant("dmma_d_C_128x128x16_w32x32"); return launch_cfg<CfgC, false>(p, s, a, b, ep);
-    case 3: note_variant("dmma_d_D_128x64x32_w32x32_2cta"); return launch_cfg<CfgD, false>(p, s, a, b, ep);
-    default: note_variant("dmma_d_B_128x64x16_w32x32_2cta"); return launch_cfg<CfgB, false>(p, s, a, b, ep);
+  note_variant("dmma_d_128x64x16_w32x32_2cta");
+  switch (amode) {
+    case LD_DIM16: return launch_b<false, LD_DIM16>(bmode, p, s, a, b, ep);
+    case LD_DIM8: return launch_b<false, LD_DIM8>(bmode, p, s, a, b, ep);
+    default: return launch_b<false, LD_K>(bmode, p, s, a, b, ep);
   }
 }
 
