@@ -25,9 +25,12 @@
 namespace b200 {
 namespace {
 
-template <int BM_, int BN_, int WM_, int WN_, int MINB_, int BK_ = 16, int STAGES_ = 4>
+template <int BM_, int BN_, int WM_, int WN_, int MINB_, int BK_ = 16, int STAGES_ = 4, bool MBAR_ = false>
 struct Cfg {
   static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, MINB = MINB_, BK = BK_, STAGES = STAGES_;
+  // MBAR: per-stage full/empty mbarriers instead of one __syncthreads per k-tile.  Copies run two tiles ahead in a
+  // four-stage ring, so a warp only waits for warps that are more than a whole tile behind it.
+  static constexpr bool MBAR = MBAR_;
   static constexpr int WARPS_M = BM / WM, WARPS_N = BN / WN;
   static constexpr int THREADS = WARPS_M * WARPS_N * 32;
   static constexpr int MI = WM / 8, NJ = WN / 8;
@@ -114,6 +117,25 @@ __device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, dou
                : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  const uint32_t a = smem_u32(bar);
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive on `bar` once all cp.async copies issued so far by this thread have landed (no pending-count increment)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 struct EpiParams {
   double alpha[2], beta[2];
   int beta_zero;
@@ -167,7 +189,6 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
   auto load_all = [&](int64_t kt) {
     double* sa = As + (kt % STAGES) * C::PANEL_A;
     double* sb = Bs + (kt % STAGES) * C::PANEL_B;
-#pragma unroll
     const int64_t rem = k - kt * BK;
     const int krem = rem > (1 << 20) ? (1 << 20) : (int)rem;
     const double* pa = la.tile_ptr(a, kt);
@@ -177,26 +198,45 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
     for (int e = 0; e < LB::E; ++e) lb.copy(sb, b, e, pb, krem);
   };
+  constexpr int LOOK = C::MBAR ? STAGES - 2 : STAGES - 1;   // tiles in flight ahead of the one being multiplied
+  __shared__ uint64_t full_bar[C::MBAR ? STAGES : 1], empty_bar[C::MBAR ? STAGES : 1];
+  if constexpr (C::MBAR) {
+    if (tid == 0) {
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) {
-    if (s < nkt) load_all(s);
-    cp_async_commit();
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], C::THREADS); mbar_init(&empty_bar[s], C::THREADS / 32); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int s = 0; s < LOOK; ++s) {
+    if (s < nkt) {
+      load_all(s);
+      if constexpr (C::MBAR) cp_async_mbar_arrive(&full_bar[s]);
+    }
+    if constexpr (!C::MBAR) cp_async_commit();
   }
 
   const int fr = lane >> 2, fk = lane & 3;  // fragment row (0..7) and k (0..3) of this lane
   for (int64_t kt = 0; kt < nkt; ++kt) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    const int64_t nxt = kt + STAGES - 1;
+    const int64_t nxt = kt + LOOK;
     const bool do_load = nxt < nkt;
-    double* sa_n = As + (nxt % STAGES) * C::PANEL_A;
-    double* sb_n = Bs + (nxt % STAGES) * C::PANEL_B;
+    const int st = (int)(kt % STAGES), sn = (int)(nxt % STAGES);
+    if constexpr (C::MBAR) {
+      // the ring slot of tile nxt was last read by tile nxt - STAGES: every warp must have released it
+      if (do_load && nxt >= STAGES) mbar_wait(&empty_bar[sn], (uint32_t)((nxt / STAGES - 1) & 1));
+      mbar_wait(&full_bar[st], (uint32_t)((kt / STAGES) & 1));
+    } else {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+    }
+    double* sa_n = As + sn * C::PANEL_A;
+    double* sb_n = Bs + sn * C::PANEL_B;
     const int64_t rem_n = k - nxt * BK;
     const int krem_n = rem_n > (1 << 20) ? (1 << 20) : (int)rem_n;
     const double* pa_n = la.tile_ptr(a, nxt);
     const double* pb_n = lb.tile_ptr(b, nxt);
-    const double* As_ = As + (kt % STAGES) * C::PANEL_A + wm * C::WM + fr;
-    const double* Bs_ = Bs + (kt % STAGES) * C::PANEL_B + wn * C::WN + fr;
+    const double* As_ = As + st * C::PANEL_A + wm * C::WM + fr;
+    const double* Bs_ = Bs + st * C::PANEL_B + wn * C::WN + fr;
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; ++k4) {
       double af[MI], bf[NJ];
@@ -219,7 +259,13 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
         for (int j = 0; j < NJ; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
     }
-    cp_async_commit();
+    if constexpr (C::MBAR) {
+      if (do_load) cp_async_mbar_arrive(&full_bar[sn]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);   // this warp has read everything it needs from slot st
+    } else {
+      cp_async_commit();
+    }
   }
   cp_async_wait<0>();
 
@@ -280,7 +326,8 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 // 128x64x16 tile, 8 warps of 32x32, 4-stage ring, 2 CTAs / SM: the two co-resident CTAs cover each other's barrier,
 // prologue and epilogue bubbles (profiles/variant_sweep_r01.md: wins or ties against 128x128 / 1 CTA per SM).
-using CfgB = Cfg<128, 64, 32, 32, 2, 16, 4>;
+using CfgB = Cfg<128, 64, 32, 32, 2, 16, 4, false>;
+using CfgM = Cfg<128, 64, 32, 32, 2, 16, 4, true>;   // same tile, mbarrier pipeline (B200BLAS_DMMA_SYNC=mbar)
 
 template <typename C, bool CPLX, int AMODE, int BMODE>
 int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
@@ -299,17 +346,33 @@ int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const Pa
   return (int)cudaGetLastError();
 }
 
-template <bool CPLX, int AMODE>
+template <typename CF, bool CPLX, int AMODE>
 int launch_b(int bmode, const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
   if constexpr (CPLX) {
-    return bmode == LD_K ? launch_cfg<CfgB, true, AMODE, LD_K>(p, s, a, b, ep) : launch_cfg<CfgB, true, AMODE, LD_DIM16>(p, s, a, b, ep);
+    return bmode == LD_K ? launch_cfg<CF, true, AMODE, LD_K>(p, s, a, b, ep) : launch_cfg<CF, true, AMODE, LD_DIM16>(p, s, a, b, ep);
   } else {
     switch (bmode) {
-      case LD_DIM16: return launch_cfg<CfgB, false, AMODE, LD_DIM16>(p, s, a, b, ep);
-      case LD_DIM8: return launch_cfg<CfgB, false, AMODE, LD_DIM8>(p, s, a, b, ep);
-      default: return launch_cfg<CfgB, false, AMODE, LD_K>(p, s, a, b, ep);
+      case LD_DIM16: return launch_cfg<CF, false, AMODE, LD_DIM16>(p, s, a, b, ep);
+      case LD_DIM8: return launch_cfg<CF, false, AMODE, LD_DIM8>(p, s, a, b, ep);
+      default: return launch_cfg<CF, false, AMODE, LD_K>(p, s, a, b, ep);
     }
   }
+}
+
+template <typename CF>
+int launch_modes(bool cplx, int amode, int bmode, const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b,
+                 const EpiParams& ep) {
+  if (cplx) return amode == LD_K ? launch_b<CF, true, LD_K>(bmode, p, s, a, b, ep) : launch_b<CF, true, LD_DIM16>(bmode, p, s, a, b, ep);
+  switch (amode) {
+    case LD_DIM16: return launch_b<CF, false, LD_DIM16>(bmode, p, s, a, b, ep);
+    case LD_DIM8: return launch_b<CF, false, LD_DIM8>(bmode, p, s, a, b, ep);
+    default: return launch_b<CF, false, LD_K>(bmode, p, s, a, b, ep);
+  }
+}
+
+bool use_mbar() {
+  static const bool v = [] { const char* e = getenv("B200BLAS_DMMA_SYNC"); return e && e[0] == 'm'; }();
+  return v;
 }
 
 }  // namespace
@@ -338,16 +401,12 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
   // loader modes: 16-byte copies need the tile dimension contiguous, a 16-byte aligned base and (real) an even ld
   const int amode = !a.dim_contig ? LD_K : (a.vec16 ? LD_DIM16 : LD_DIM8);
   const int bmode = !b.dim_contig ? LD_K : (b.vec16 ? LD_DIM16 : LD_DIM8);
-  if (cplx) {
-    note_variant("dmma_z_64x32x16_w16x16_2cta");
-    return amode == LD_K ? launch_b<true, LD_K>(bmode, p, s, a, b, ep) : launch_b<true, LD_DIM16>(bmode, p, s, a, b, ep);
+  if (use_mbar()) {
+    note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta_mbar" : "dmma_d_128x64x16_w32x32_2cta_mbar");
+    return launch_modes<CfgM>(cplx, amode, bmode, p, s, a, b, ep);
   }
-  note_variant("dmma_d_128x64x16_w32x32_2cta");
-  switch (amode) {
-    case LD_DIM16: return launch_b<false, LD_DIM16>(bmode, p, s, a, b, ep);
-    case LD_DIM8: return launch_b<false, LD_DIM8>(bmode, p, s, a, b, ep);
-    default: return launch_b<false, LD_K>(bmode, p, s, a, b, ep);
-  }
+  note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta" : "dmma_d_128x64x16_w32x32_2cta");
+  return launch_modes<CfgB>(cplx, amode, bmode, p, s, a, b, ep);
 }
 
 }  // namespace b200

@@ -132,7 +132,16 @@ struct Tf32Params {
   float alpha, beta;
   int beta_zero;
   int64_t tiles_m, tiles_n;
+  int kchunk;  // k-blocks accumulated in TMEM before the partial sum is folded into C (see KCHUNK_DEFAULT)
 };
+
+// The tensor core adds into the fp32 TMEM accumulator without round-to-nearest; over a long k the truncation
+// bias grows linearly (measured: gauge ratio 34 at k = 8192 for one uninterrupted chain).  The chain is therefore
+// cut every KCHUNK_DEFAULT*32 k values: the epilogue warps fold each partial sum into C with IEEE fp32 adds
+// (C = alpha*acc + beta*C for the first chunk, C += alpha*acc afterwards) while the next chunk accumulates in the
+// other TMEM buffer.  Same idea as the reference's kc blocking, where every kc block ends in one FMA into C
+// (GeneralBlockPanelKernel.h:1025-1066).
+constexpr int KCHUNK_DEFAULT = 32;
 
 constexpr int GROUP = 16;  // tile rasterisation: a wave of 148 tiles covers ~16 x 9 tiles (2048 x 2304 of C): balanced A/B panel reuse in L2
 __device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t tiles_n, int64_t& tm, int64_t& tn) {
@@ -211,27 +220,30 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(tempty(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full(stage), phase);
+        for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {   // one accumulation chunk per TMEM buffer
+          mbar_wait(tempty(acc), acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t s0 = base + stage * STAGE_BYTES;
-          const uint64_t a_hi = umma_desc_sw128(s0), a_lo = umma_desc_sw128(s0 + A_PLANE);
-          const uint64_t b_hi = umma_desc_sw128(s0 + 2 * A_PLANE), b_lo = umma_desc_sw128(s0 + 2 * A_PLANE + B_PLANE);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
+          const int kb1 = kb0 + p.kchunk < nkb ? kb0 + p.kchunk : nkb;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full(stage), phase);
+            tc_fence_after();
+            const uint32_t s0 = base + stage * STAGE_BYTES;
+            const uint64_t a_hi = umma_desc_sw128(s0), a_lo = umma_desc_sw128(s0 + A_PLANE);
+            const uint64_t b_hi = umma_desc_sw128(s0 + 2 * A_PLANE), b_lo = umma_desc_sw128(s0 + 2 * A_PLANE + B_PLANE);
 #pragma unroll
-          for (int k8 = 0; k8 < TK / UK; ++k8) {
-            const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);  // advance inside the 128-byte swizzle atom
-            tc_mma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, (kb | k8) != 0);
-            tc_mma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
-            tc_mma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+            for (int k8 = 0; k8 < TK / UK; ++k8) {
+              const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);  // advance inside the 128-byte swizzle atom
+              tc_mma_tf32(d_tmem, a_lo + off, b_hi + off, idesc, ((kb - kb0) | k8) != 0);
+              tc_mma_tf32(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+              tc_mma_tf32(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+            }
+            tc_commit(empty(stage));  // frees the smem stage once these MMAs have read it
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(empty(stage));  // frees the smem stage once these MMAs have read it
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+          tc_commit(tfull(acc));  // partial sum complete -> epilogue
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        tc_commit(tfull(acc));  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -242,32 +254,37 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
-      mbar_wait(tfull(acc), acc_phase);
-      tc_fence_after();
       const int64_t row = tm * TM + q * 32 + lane;
       float* crow = p.C + row;
+      for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
+        // first chunk: C = alpha*acc + beta*C (beta == 0: C is not read); later chunks: C += alpha*acc
+        const float beta = kb0 == 0 ? p.beta : 1.f;
+        const bool read_c = kb0 != 0 || !p.beta_zero;
+        mbar_wait(tfull(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (uint32_t)(acc * TN + c0) + ((uint32_t)(q * 32) << 16), r);
-        const int64_t col0 = tn * TN + c0;
-        if (row < p.m) {
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + (uint32_t)(acc * TN + c0) + ((uint32_t)(q * 32) << 16), r);
+          const int64_t col0 = tn * TN + c0;
+          if (row < p.m) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t col = col0 + j;
-            if (col < p.n) {
-              float v = p.alpha * __uint_as_float(r[j]);
-              float* pc = crow + col * p.ldc;
-              if (!p.beta_zero) v = fmaf(p.beta, *pc, v);
-              *pc = v;
+            for (int j = 0; j < 32; ++j) {
+              const int64_t col = col0 + j;
+              if (col < p.n) {
+                float v = p.alpha * __uint_as_float(r[j]);
+                float* pc = crow + col * p.ldc;
+                if (read_c) v = fmaf(beta, *pc, v);
+                *pc = v;
+              }
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -494,6 +511,7 @@ struct CTf32Params {
   float2 alpha, beta;
   int beta_zero;
   int64_t tiles_m, tiles_n;
+  int kchunk;
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -559,43 +577,46 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        mbar_wait(tempty(acc), acc_phase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_re = tmem_base + (uint32_t)(acc * 2 * CTN), d_im = d_re + CTN;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(full(stage), phase);
+        for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
+          mbar_wait(tempty(acc), acc_phase ^ 1u);
           tc_fence_after();
-          const uint32_t s0 = base + stage * CSTAGE_BYTES;
-          uint64_t a[4], b[4];
+          const uint32_t d_re = tmem_base + (uint32_t)(acc * 2 * CTN), d_im = d_re + CTN;
+          const int kb1 = kb0 + p.kchunk < nkb ? kb0 + p.kchunk : nkb;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full(stage), phase);
+            tc_fence_after();
+            const uint32_t s0 = base + stage * CSTAGE_BYTES;
+            uint64_t a[4], b[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { a[i] = umma_desc_sw128(s0 + i * A_PLANE); b[i] = umma_desc_sw128(s0 + 4 * A_PLANE + i * CB_PLANE); }
-          // index: 0 = re_hi, 1 = re_lo, 2 = im_hi, 3 = im_lo
+            for (int i = 0; i < 4; ++i) { a[i] = umma_desc_sw128(s0 + i * A_PLANE); b[i] = umma_desc_sw128(s0 + 4 * A_PLANE + i * CB_PLANE); }
+            // index: 0 = re_hi, 1 = re_lo, 2 = im_hi, 3 = im_lo
 #pragma unroll
-          for (int k8 = 0; k8 < TK / UK; ++k8) {
-            const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);
-            const uint32_t first = (kb | k8) != 0;
-            // Re += Ar.Br
-            tc_mma_tf32(d_re, a[1] + off, b[0] + off, idesc, first);
-            tc_mma_tf32(d_re, a[0] + off, b[1] + off, idesc, 1u);
-            tc_mma_tf32(d_re, a[0] + off, b[0] + off, idesc, 1u);
-            // Re -= Ai.Bi
-            tc_mma_tf32(d_re, a[3] + off, b[2] + off, idesc_neg, 1u);
-            tc_mma_tf32(d_re, a[2] + off, b[3] + off, idesc_neg, 1u);
-            tc_mma_tf32(d_re, a[2] + off, b[2] + off, idesc_neg, 1u);
-            // Im += Ar.Bi
-            tc_mma_tf32(d_im, a[1] + off, b[2] + off, idesc, first);
-            tc_mma_tf32(d_im, a[0] + off, b[3] + off, idesc, 1u);
-            tc_mma_tf32(d_im, a[0] + off, b[2] + off, idesc, 1u);
-            // Im += Ai.Br
-            tc_mma_tf32(d_im, a[3] + off, b[0] + off, idesc, 1u);
-            tc_mma_tf32(d_im, a[2] + off, b[1] + off, idesc, 1u);
-            tc_mma_tf32(d_im, a[2] + off, b[0] + off, idesc, 1u);
+            for (int k8 = 0; k8 < TK / UK; ++k8) {
+              const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);
+              const uint32_t first = ((kb - kb0) | k8) != 0;
+              // Re += Ar.Br
+              tc_mma_tf32(d_re, a[1] + off, b[0] + off, idesc, first);
+              tc_mma_tf32(d_re, a[0] + off, b[1] + off, idesc, 1u);
+              tc_mma_tf32(d_re, a[0] + off, b[0] + off, idesc, 1u);
+              // Re -= Ai.Bi
+              tc_mma_tf32(d_re, a[3] + off, b[2] + off, idesc_neg, 1u);
+              tc_mma_tf32(d_re, a[2] + off, b[3] + off, idesc_neg, 1u);
+              tc_mma_tf32(d_re, a[2] + off, b[2] + off, idesc_neg, 1u);
+              // Im += Ar.Bi
+              tc_mma_tf32(d_im, a[1] + off, b[2] + off, idesc, first);
+              tc_mma_tf32(d_im, a[0] + off, b[3] + off, idesc, 1u);
+              tc_mma_tf32(d_im, a[0] + off, b[2] + off, idesc, 1u);
+              // Im += Ai.Br
+              tc_mma_tf32(d_im, a[3] + off, b[0] + off, idesc, 1u);
+              tc_mma_tf32(d_im, a[2] + off, b[1] + off, idesc, 1u);
+              tc_mma_tf32(d_im, a[2] + off, b[0] + off, idesc, 1u);
+            }
+            tc_commit(empty(stage));
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
           }
-          tc_commit(empty(stage));
-          if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+          tc_commit(tfull(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        tc_commit(tfull(acc));
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -605,39 +626,43 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
-      mbar_wait(tfull(acc), acc_phase);
-      tc_fence_after();
       const int64_t row = tm * TM + q * 32 + lane;
       float2* crow = p.C + row;
+      for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
+        const float2 beta = kb0 == 0 ? p.beta : make_float2(1.f, 0.f);
+        const bool read_c = kb0 != 0 || !p.beta_zero;
+        mbar_wait(tfull(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < CTN; c0 += 32) {
-        uint32_t re[32], im[32];
-        const uint32_t t0 = tmem_base + (uint32_t)(acc * 2 * CTN + c0) + ((uint32_t)(q * 32) << 16);
-        tmem_ld32(t0, re);
-        tmem_ld32(t0 + CTN, im);
-        const int64_t col0 = tn * CTN + c0;
-        if (row < p.m) {
+        for (int c0 = 0; c0 < CTN; c0 += 32) {
+          uint32_t re[32], im[32];
+          const uint32_t t0 = tmem_base + (uint32_t)(acc * 2 * CTN + c0) + ((uint32_t)(q * 32) << 16);
+          tmem_ld32(t0, re);
+          tmem_ld32(t0 + CTN, im);
+          const int64_t col0 = tn * CTN + c0;
+          if (row < p.m) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t col = col0 + j;
-            if (col < p.n) {
-              const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
-              float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
-              float2* pc = crow + col * p.ldc;
-              if (!p.beta_zero) {
-                const float2 o = *pc;
-                v.x += fmaf(p.beta.x, o.x, -p.beta.y * o.y);
-                v.y += fmaf(p.beta.x, o.y, p.beta.y * o.x);
+            for (int j = 0; j < 32; ++j) {
+              const int64_t col = col0 + j;
+              if (col < p.n) {
+                const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
+                float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
+                float2* pc = crow + col * p.ldc;
+                if (read_c) {
+                  const float2 o = *pc;
+                  v.x += fmaf(beta.x, o.x, -beta.y * o.y);
+                  v.y += fmaf(beta.x, o.y, beta.y * o.x);
+                }
+                *pc = v;
               }
-              *pc = v;
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -727,6 +752,10 @@ int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64
 }
 
 int64_t kpad(int64_t k) { return (k + 31) / 32 * 32; }
+int kchunk_blocks() {
+  static const int v = [] { const char* e = getenv("B200BLAS_TF32_KCHUNK"); const int x = e ? atoi(e) : 0; return x > 0 ? x : KCHUNK_DEFAULT; }();
+  return v;
+}
 int sm_count() {
   static int sms = [] {
     int dev = 0, n = 0;
@@ -783,6 +812,7 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
   prm.beta = make_float2((float)p.beta[0], (float)p.beta[1]);
   prm.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + CTN - 1) / CTN;
+  prm.kchunk = kchunk_blocks();
   static bool attr_done = false;
   if (!attr_done) {
     B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM_BYTES));
@@ -833,6 +863,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     prm.alpha = (float)p.alpha[0]; prm.beta = (float)p.beta[0];
     prm.beta_zero = (p.beta[0] == 0.0);
     prm.tiles_m = (p.m + TM2 - 1) / TM2; prm.tiles_n = (p.n + TN - 1) / TN;
+    prm.kchunk = 1 << 30;
     static bool attr2_done = false;
     if (!attr2_done) {
       B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -855,6 +886,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
   prm.alpha = (float)p.alpha[0]; prm.beta = (float)p.beta[0];
   prm.beta_zero = (p.beta[0] == 0.0);
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + TN - 1) / TN;
+  prm.kchunk = kchunk_blocks();
   static bool attr_done = false;
   if (!attr_done) {
     B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
