@@ -37,8 +37,8 @@ void note_variant(const char* name);
 
 #define B200_CUDA_TRY(expr)                                  \
   do {                                                       \
-    cudaError_t _e = (expr);                                 \
-    if (_e != cudaSuccess) return (int)_e;                   \
+    const int _e = (int)(expr);                              \
+    if (_e != 0) return _e;                                  \
   } while (0)
 
 // ---- device helpers ---------------------------------------------------------------------------------------

@@ -274,21 +274,29 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
   if constexpr (!CPLX) {
     const double alpha = ep.alpha[0], beta = ep.beta[0];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j)
+    for (int j = 0; j < NJ; ++j) {
+      // loads of this column pair first, stores afterwards: a load placed after a store through the same pointer
+      // cannot be hoisted by the compiler, which would serialise every read-modify-write round trip
+      double old[2][MI];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int64_t gj = n0 + wn * C::WN + j * 8 + 2 * fk + c;
-        if (gj >= n) continue;
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
           const int64_t gi = m0 + wm * C::WM + i * 8 + fr;
-          if (gi >= m) continue;
-          double* pc = Cmat + gi + gj * ldc;
-          double r = alpha * acc[i][j][c];
-          if (!ep.beta_zero) r = fma(beta, *pc, r);
-          *pc = r;
+          old[c][i] = (!ep.beta_zero && gi < m && gj < n) ? Cmat[gi + gj * ldc] : 0.0;
         }
       }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int64_t gj = n0 + wn * C::WN + j * 8 + 2 * fk + c;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int64_t gi = m0 + wm * C::WM + i * 8 + fr;
+          if (gi < m && gj < n) Cmat[gi + gj * ldc] = fma(beta, old[c][i], alpha * acc[i][j][c]);
+        }
+      }
+    }
   } else {
     // lanes (l, l^4) hold the Ar-row and the Ai-row of one complex row; c0 = x.Br, c1 = x.Bi
     const bool odd = fr & 1;  // this lane holds the Ai row
@@ -299,24 +307,36 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int64_t gj = n0 + wn * (C::WN / 2) + j * 4 + fk;  // complex column
+      double outv[MI];
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
-        const int64_t gi = m0 + wm * (C::WM / 2) + i * 4 + (fr >> 1);  // complex row
         const double c0 = acc[i][j][0], c1 = acc[i][j][1];
         const double o1 = __shfl_xor_sync(0xffffffffu, c1, 4);
         // even lane: re = P + sS*S (P = own c0, S = partner c1); odd lane: im = sQ*Q + sR*R (Q = partner c1, R = own c0)
         const double mine = odd ? fma(sQ, o1, sR * c0) : fma(sS, o1, c0);
         const double other = __shfl_xor_sync(0xffffffffu, mine, 4);
         const double re = odd ? other : mine, im = odd ? mine : other;
-        if (gi >= m || gj >= n) continue;
-        double* pc = Cmat + 2 * (gi + gj * ldc);
         // out = alpha*(re,im) + beta*Cold ; even lane stores the real part, odd lane the imaginary part
-        double out = odd ? fma(ep.alpha[0], im, ep.alpha[1] * re) : fma(ep.alpha[0], re, -ep.alpha[1] * im);
-        if (!ep.beta_zero) {
-          const double cr = pc[0], ci = pc[1];
-          out += odd ? fma(ep.beta[0], ci, ep.beta[1] * cr) : fma(ep.beta[0], cr, -ep.beta[1] * ci);
+        outv[i] = odd ? fma(ep.alpha[0], im, ep.alpha[1] * re) : fma(ep.alpha[0], re, -ep.alpha[1] * im);
+      }
+      // loads of the whole column first, stores afterwards (no load is stuck behind a store to the same array)
+      if (!ep.beta_zero) {
+        double cr[MI], ci[MI];
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+          const int64_t gi = m0 + wm * (C::WM / 2) + i * 4 + (fr >> 1);
+          const bool ok = gi < m && gj < n;
+          cr[i] = ok ? Cmat[2 * (gi + gj * ldc)] : 0.0;
+          ci[i] = ok ? Cmat[2 * (gi + gj * ldc) + 1] : 0.0;
         }
-        pc[odd ? 1 : 0] = out;
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+          outv[i] += odd ? fma(ep.beta[0], ci[i], ep.beta[1] * cr[i]) : fma(ep.beta[0], cr[i], -ep.beta[1] * ci[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        const int64_t gi = m0 + wm * (C::WM / 2) + i * 4 + (fr >> 1);
+        if (gi < m && gj < n) Cmat[2 * (gi + gj * ldc) + (odd ? 1 : 0)] = outv[i];
       }
     }
   }
@@ -371,7 +391,8 @@ int launch_modes(bool cplx, int amode, int bmode, const GemmProblem& p, cudaStre
 }
 
 bool use_mbar() {
-  static const bool v = [] { const char* e = getenv("B200BLAS_DMMA_SYNC"); return e && e[0] == 'm'; }();
+  // default: mbarrier pipeline (<= 1.5 % faster than __syncthreads in profiles/variant_sweep_r01.md); "B200BLAS_DMMA_SYNC=bar" selects the other
+  static const bool v = [] { const char* e = getenv("B200BLAS_DMMA_SYNC"); return !(e && e[0] == 'b'); }();
   return v;
 }
 

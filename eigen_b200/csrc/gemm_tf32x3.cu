@@ -141,7 +141,7 @@ struct Tf32Params {
 // (C = alpha*acc + beta*C for the first chunk, C += alpha*acc afterwards) while the next chunk accumulates in the
 // other TMEM buffer.  Same idea as the reference's kc blocking, where every kc block ends in one FMA into C
 // (GeneralBlockPanelKernel.h:1025-1066).
-constexpr int KCHUNK_DEFAULT = 32;
+constexpr int KCHUNK_DEFAULT = 8;
 
 constexpr int GROUP = 16;  // tile rasterisation: a wave of 148 tiles covers ~16 x 9 tiles (2048 x 2304 of C): balanced A/B panel reuse in L2
 __device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t tiles_n, int64_t& tm, int64_t& tn) {
@@ -268,16 +268,14 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           tmem_ld32(tmem_base + (uint32_t)(acc * TN + c0) + ((uint32_t)(q * 32) << 16), r);
           const int64_t col0 = tn * TN + c0;
           if (row < p.m) {
+            // all loads of the 32 columns first, then all stores: a load placed after a store through the same
+            // pointer cannot be hoisted by the compiler, which would serialise 32 memory round trips
+            float old[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t col = col0 + j;
-              if (col < p.n) {
-                float v = p.alpha * __uint_as_float(r[j]);
-                float* pc = crow + col * p.ldc;
-                if (read_c) v = fmaf(beta, *pc, v);
-                *pc = v;
-              }
-            }
+            for (int j = 0; j < 32; ++j) old[j] = (read_c && col0 + j < p.n) ? crow[(col0 + j) * p.ldc] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) crow[(col0 + j) * p.ldc] = fmaf(beta, old[j], p.alpha * __uint_as_float(r[j]));
           }
         }
         tc_fence_before();
@@ -423,16 +421,12 @@ tf32x3_gemm256_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
           tmem_ld32(tmem_base + (uint32_t)(h * TN + c0) + ((uint32_t)(q * 32) << 16), r);
           const int64_t col0 = tn * TN + c0;
           if (row < p.m) {
+            float old[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t col = col0 + j;
-              if (col < p.n) {
-                float v = p.alpha * __uint_as_float(r[j]);
-                float* pc = crow + col * p.ldc;
-                if (!p.beta_zero) v = fmaf(p.beta, *pc, v);
-                *pc = v;
-              }
-            }
+            for (int j = 0; j < 32; ++j) old[j] = (!p.beta_zero && col0 + j < p.n) ? crow[(col0 + j) * p.ldc] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.n) crow[(col0 + j) * p.ldc] = fmaf(p.beta, old[j], p.alpha * __uint_as_float(r[j]));
           }
         }
       }
@@ -641,19 +635,22 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
           tmem_ld32(t0 + CTN, im);
           const int64_t col0 = tn * CTN + c0;
           if (row < p.m) {
+            // loads first, stores afterwards (see the real kernel); 16 columns at a time to bound registers
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t col = col0 + j;
-              if (col < p.n) {
-                const float xr = __uint_as_float(re[j]), xi = __uint_as_float(im[j]);
-                float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
-                float2* pc = crow + col * p.ldc;
-                if (read_c) {
-                  const float2 o = *pc;
-                  v.x += fmaf(beta.x, o.x, -beta.y * o.y);
-                  v.y += fmaf(beta.x, o.y, beta.y * o.x);
+            for (int h = 0; h < 32; h += 16) {
+              float2 old[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                old[j] = (read_c && col0 + h + j < p.n) ? crow[(col0 + h + j) * p.ldc] : make_float2(0.f, 0.f);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (col0 + h + j < p.n) {
+                  const float xr = __uint_as_float(re[h + j]), xi = __uint_as_float(im[h + j]);
+                  float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
+                  v.x += fmaf(beta.x, old[j].x, -beta.y * old[j].y);
+                  v.y += fmaf(beta.x, old[j].y, beta.y * old[j].x);
+                  crow[(col0 + h + j) * p.ldc] = v;
                 }
-                *pc = v;
               }
             }
           }

@@ -9,10 +9,13 @@
 // upload of slab j+1, the product on slab j and the download of slab j-1 overlap (the GPU analogue of the kc/nc
 // panel streaming of GeneralMatrixMatrix.h:155-198).  There is no CPU fallback.
 #include <atomic>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/b200blas.h"
 #include "common.cuh"
@@ -127,6 +130,176 @@ static void load_scalar(int type, const void* p, double out[2]) {
   }
 }
 
+// ---- pageable operands: pinned staging ring + copy workers -------------------------------------------------------
+// Eigen matrices are ordinary pageable memory.  A cudaMemcpy2DAsync from pageable memory is staged by the driver in
+// small synchronous pieces (~11 GB/s measured through bench_gemm -DHAVE_BLAS).  Instead, worker threads copy the
+// operand into a ring of pinned buffers (several threads are needed to outrun one PCIe Gen5 x16 link) and each filled
+// buffer goes to the device with one asynchronous 2-D DMA while the workers fill the next one.
+class CopyPool {
+ public:
+  explicit CopyPool(int nthreads) : stop_(false), gen_(0), pending_(0) {
+    for (int i = 0; i < nthreads; ++i) th_.emplace_back([this] { worker(); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> l(mu_); stop_ = true; ++gen_; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // dst/src 2-D regions of `ncols` columns of `width` bytes with the given pitches; returns when the copy is done
+  void copy2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t ncols) {
+    if (width * ncols < (1u << 20) || th_.empty()) {
+      for (size_t j = 0; j < ncols; ++j) memcpy(dst + j * dpitch, src + j * spitch, width);
+      return;
+    }
+    std::unique_lock<std::mutex> call(call_mu_);  // one parallel copy at a time
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      job_ = {dst, dpitch, src, spitch, width, ncols};
+      // split every column into pieces of <= 1 MiB so that tall-and-thin regions parallelise as well
+      piece_ = width > (1u << 20) ? (1u << 20) : width;
+      pieces_per_col_ = (width + piece_ - 1) / piece_;
+      next_.store(0);
+      total_ = ncols * pieces_per_col_;
+      pending_ = (int)th_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    run();  // the caller works too
+    std::unique_lock<std::mutex> l(mu_);
+    done_cv_.wait(l, [this] { return pending_ == 0; });
+  }
+
+ private:
+  struct Job { char* dst; size_t dpitch; const char* src; size_t spitch; size_t width; size_t ncols; };
+  void run() {
+    for (;;) {
+      const size_t i = next_.fetch_add(1);
+      if (i >= total_) break;
+      const size_t col = i / pieces_per_col_, off = (i % pieces_per_col_) * piece_;
+      const size_t len = off + piece_ <= job_.width ? piece_ : job_.width - off;
+      memcpy(job_.dst + col * job_.dpitch + off, job_.src + col * job_.spitch + off, len);
+    }
+  }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      run();
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--pending_ == 0) done_cv_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, done_cv_;
+  bool stop_;
+  uint64_t gen_;
+  int pending_;
+  Job job_{};
+  size_t piece_ = 0, pieces_per_col_ = 1, total_ = 0;
+  std::atomic<size_t> next_{0};
+};
+
+static CopyPool& copy_pool() {
+  static CopyPool pool([] {
+    const char* e = getenv("B200BLAS_COPY_THREADS");
+    int n = e ? atoi(e) : 0;
+    if (n <= 0) {
+      const unsigned hc = std::thread::hardware_concurrency();
+      n = hc >= 16 ? 7 : hc >= 8 ? 5 : hc >= 4 ? 3 : 1;
+    }
+    return n - 1 < 0 ? 0 : n - 1;  // the calling thread is the n-th copier
+  }());
+  return pool;
+}
+
+static bool is_pageable(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered;
+}
+
+struct PinnedRing {
+  static constexpr int NBUF = 4;
+  static constexpr size_t BYTES = (size_t)32 << 20;
+  char* buf[NBUF] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t free_ev[NBUF];
+  bool used[NBUF] = {false, false, false, false};
+  int next = 0;
+  bool ready = false;
+  int init() {
+    if (ready) return 0;
+    for (int i = 0; i < NBUF; ++i) {
+      B200_CUDA_TRY(cudaHostAlloc((void**)&buf[i], BYTES, cudaHostAllocDefault));
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
+    }
+    ready = true;
+    return 0;
+  }
+  void release() {
+    if (!ready) return;
+    for (int i = 0; i < NBUF; ++i) { cudaFreeHost(buf[i]); cudaEventDestroy(free_ev[i]); buf[i] = nullptr; used[i] = false; }
+    ready = false;
+  }
+  // host (pageable) -> device, 2-D, through the ring; asynchronous with respect to the device stream
+  int h2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t ncols, cudaStream_t s) {
+    if (width == 0 || ncols == 0) return 0;
+    if (width > BYTES) return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, ncols, cudaMemcpyHostToDevice, s);
+    { const int e = init(); if (e) return e; }
+    const size_t cols_per = BYTES / width;
+    for (size_t c0 = 0; c0 < ncols; c0 += cols_per) {
+      const size_t nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
+      const int slot = next;
+      next = (next + 1) % NBUF;
+      if (used[slot]) B200_CUDA_TRY(cudaEventSynchronize(free_ev[slot]));
+      copy_pool().copy2d(buf[slot], width, src + c0 * spitch, spitch, width, nc);
+      B200_CUDA_TRY(cudaMemcpy2DAsync(dst + c0 * dpitch, dpitch, buf[slot], width, width, nc, cudaMemcpyHostToDevice, s));
+      B200_CUDA_TRY(cudaEventRecord(free_ev[slot], s));
+      used[slot] = true;
+    }
+    return 0;
+  }
+  // device -> host (pageable), 2-D, through the ring; returns when the data is in the caller's memory
+  int d2h(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t ncols, cudaStream_t s) {
+    if (width == 0 || ncols == 0) return 0;
+    if (width > BYTES) {
+      B200_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, ncols, cudaMemcpyDeviceToHost, s));
+      return (int)cudaStreamSynchronize(s);
+    }
+    { const int e = init(); if (e) return e; }
+    const size_t cols_per = BYTES / width;
+    // software pipeline over the ring: DMA of chunk i+1 runs while the workers copy chunk i out
+    size_t issued = 0, retired = 0;
+    const size_t nchunks = (ncols + cols_per - 1) / cols_per;
+    int slots[NBUF];
+    while (retired < nchunks) {
+      while (issued < nchunks && issued - retired < (size_t)NBUF) {
+        const size_t c0 = issued * cols_per, nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
+        const int slot = (int)(issued % NBUF);
+        slots[slot] = slot;
+        B200_CUDA_TRY(cudaMemcpy2DAsync(buf[slot], width, src + c0 * spitch, spitch, width, nc, cudaMemcpyDeviceToHost, s));
+        B200_CUDA_TRY(cudaEventRecord(free_ev[slot], s));
+        used[slot] = false;
+        ++issued;
+      }
+      const size_t c0 = retired * cols_per, nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
+      const int slot = (int)(retired % NBUF);
+      B200_CUDA_TRY(cudaEventSynchronize(free_ev[slot]));
+      copy_pool().copy2d(dst + c0 * dpitch, dpitch, buf[slot], width, width, nc);
+      ++retired;
+    }
+    (void)slots;
+    return 0;
+  }
+};
+
 // ---- per-process staging context ---------------------------------------------------------------------------
 struct Staging {
   std::mutex mu;
@@ -138,6 +311,7 @@ struct Staging {
   static constexpr int MAX_ACHUNKS = 8;
   cudaEvent_t ev_in[MAX_SLABS], ev_comp[MAX_SLABS], ev_ac[MAX_ACHUNKS], ev_a = nullptr;
   bool ready = false;
+  PinnedRing ring_in, ring_out;   // pageable operands only
 
   int init() {
     int d = 0;
@@ -173,6 +347,8 @@ struct Staging {
     if (ev_a) cudaEventDestroy(ev_a);
     for (int i = 0; i < MAX_SLABS; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); }
     for (int i = 0; i < MAX_ACHUNKS; ++i) cudaEventDestroy(ev_ac[i]);
+    ring_in.release();
+    ring_out.release();
     s_in = s_comp = s_out = nullptr; ev_a = nullptr;
     ready = false;
   }
@@ -212,6 +388,15 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
   char* dB = (char*)st.dbuf[1];
   char* dC = (char*)st.dbuf[2];
   t_h2d = t_d2h = 0;
+  // pageable operands of at least a few MiB go through the pinned ring; pinned / small ones are copied directly
+  const size_t ring_min = (size_t)4 << 20;
+  const bool page_a = have_product && (size_t)ra * ca * es >= ring_min && is_pageable(a);
+  const bool page_b = have_product && (size_t)rb * cb * es >= ring_min && is_pageable(b);
+  const bool page_c = (size_t)m * n * es >= ring_min && is_pageable(c);
+  auto upload = [&](bool paged, char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t ncols) -> int {
+    if (paged) return st.ring_in.h2d(dst, dpitch, src, spitch, width, ncols, st.s_in);
+    return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, ncols, cudaMemcpyHostToDevice, st.s_in);
+  };
 
   // column slabs of C (and of op(B)): ~16 slabs, at least 512 columns wide, multiples of 256 columns
   const double total_bytes = (double)es * ((double)m * k + (double)k * n + 2.0 * m * n);
@@ -223,6 +408,15 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
   // A travels in k-chunks (contiguous column blocks for 'N', row blocks for 'T'/'C'); the first column slab of C
   // accumulates chunk by chunk (beta = 1 after the first) while later chunks are still on the bus, so the
   // start-up bubble is one chunk instead of all of A.  Later slabs see A resident and run at full k.
+  std::thread downloader;
+  std::mutex dl_mu;
+  std::condition_variable dl_cv;
+  int dl_ready = 0, dl_err = 0;
+  bool dl_started = false, dl_abort = false;
+  struct JoinGuard {   // never leave this function with a joinable thread (early error returns)
+    std::thread& t; std::mutex& mu; std::condition_variable& cv; bool& abort;
+    ~JoinGuard() { if (t.joinable()) { { std::lock_guard<std::mutex> l(mu); abort = true; } cv.notify_all(); t.join(); } }
+  } join_guard{downloader, dl_mu, dl_cv, dl_abort};
   int nac = 1;
   if (have_product && nslabs > 1 && k >= 8 * 512) nac = Staging::MAX_ACHUNKS;
   const int64_t kch = round_up((k + nac - 1) / nac, 256);
@@ -230,11 +424,11 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
     const int64_t k0 = (int64_t)c * kch, kc = std::min<int64_t>(kch, k - k0);
     if (kc <= 0) return 0;
     if (opa == OP_N) {
-      B200_CUDA_TRY(cudaMemcpy2DAsync(dA + (size_t)k0 * dlda * es, (size_t)dlda * es, (const char*)a + (size_t)k0 * lda * es,
-                                      (size_t)lda * es, (size_t)m * es, (size_t)kc, cudaMemcpyHostToDevice, st.s_in));
+      B200_CUDA_TRY(upload(page_a, dA + (size_t)k0 * dlda * es, (size_t)dlda * es, (const char*)a + (size_t)k0 * lda * es,
+                           (size_t)lda * es, (size_t)m * es, (size_t)kc));
     } else {
-      B200_CUDA_TRY(cudaMemcpy2DAsync(dA + (size_t)k0 * es, (size_t)dlda * es, (const char*)a + (size_t)k0 * es,
-                                      (size_t)lda * es, (size_t)kc * es, (size_t)m, cudaMemcpyHostToDevice, st.s_in));
+      B200_CUDA_TRY(upload(page_a, dA + (size_t)k0 * es, (size_t)dlda * es, (const char*)a + (size_t)k0 * es,
+                           (size_t)lda * es, (size_t)kc * es, (size_t)m));
     }
     t_h2d += (uint64_t)m * kc * es;
     B200_CUDA_TRY(cudaEventRecord(st.ev_ac[c], st.s_in));
@@ -244,17 +438,17 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
     const int64_t j0 = (int64_t)j * slab, nj = std::min<int64_t>(slab, n - j0);
     if (have_product) {
       if (opb == OP_N) {
-        B200_CUDA_TRY(cudaMemcpy2DAsync(dB + (size_t)j0 * dldb * es, (size_t)dldb * es, (const char*)b + (size_t)j0 * ldb * es,
-                                        (size_t)ldb * es, (size_t)k * es, (size_t)nj, cudaMemcpyHostToDevice, st.s_in));
+        B200_CUDA_TRY(upload(page_b, dB + (size_t)j0 * dldb * es, (size_t)dldb * es, (const char*)b + (size_t)j0 * ldb * es,
+                             (size_t)ldb * es, (size_t)k * es, (size_t)nj));
       } else {
-        B200_CUDA_TRY(cudaMemcpy2DAsync(dB + (size_t)j0 * es, (size_t)dldb * es, (const char*)b + (size_t)j0 * es,
-                                        (size_t)ldb * es, (size_t)nj * es, (size_t)k, cudaMemcpyHostToDevice, st.s_in));
+        B200_CUDA_TRY(upload(page_b, dB + (size_t)j0 * es, (size_t)dldb * es, (const char*)b + (size_t)j0 * es,
+                             (size_t)ldb * es, (size_t)nj * es, (size_t)k));
       }
       t_h2d += (uint64_t)k * nj * es;
     }
     if (!beta_zero) {  // beta == 0: C is never read, so it is not uploaded either (blas/level3_impl.h:64)
-      B200_CUDA_TRY(cudaMemcpy2DAsync(dC + (size_t)j0 * dldc * es, (size_t)dldc * es, (const char*)c + (size_t)j0 * ldc * es,
-                                      (size_t)ldc * es, (size_t)m * es, (size_t)nj, cudaMemcpyHostToDevice, st.s_in));
+      B200_CUDA_TRY(upload(page_c, dC + (size_t)j0 * dldc * es, (size_t)dldc * es, (const char*)c + (size_t)j0 * ldc * es,
+                           (size_t)ldc * es, (size_t)m * es, (size_t)nj));
       t_h2d += (uint64_t)m * nj * es;
     }
     B200_CUDA_TRY(cudaEventRecord(st.ev_in[j], st.s_in));
@@ -283,11 +477,40 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
       if (e) { cudaDeviceSynchronize(); return e; }
     }
     B200_CUDA_TRY(cudaEventRecord(st.ev_comp[j], st.s_comp));
-    B200_CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_comp[j], 0));
     // only the m x nj window travels back: rows m..ldc-1 of the caller's C stay untouched
-    B200_CUDA_TRY(cudaMemcpy2DAsync((char*)c + (size_t)j0 * ldc * es, (size_t)ldc * es, dC + (size_t)j0 * dldc * es,
-                                    (size_t)dldc * es, (size_t)m * es, (size_t)nj, cudaMemcpyDeviceToHost, st.s_out));
+    if (page_c) {
+      // a downloader thread drains finished slabs through the pinned ring while this thread keeps uploading
+      if (!dl_started) {
+        dl_started = true;
+        downloader = std::thread([&, dev = st.dev] {
+          cudaSetDevice(dev);
+          for (int jj = 0; jj < nslabs; ++jj) {
+            {
+              std::unique_lock<std::mutex> l(dl_mu);
+              dl_cv.wait(l, [&] { return dl_ready > jj || dl_abort; });
+              if (dl_abort) return;
+            }
+            const int64_t q0 = (int64_t)jj * slab, nq = std::min<int64_t>(slab, n - q0);
+            int e = (int)cudaEventSynchronize(st.ev_comp[jj]);
+            if (!e) e = st.ring_out.d2h((char*)c + (size_t)q0 * ldc * es, (size_t)ldc * es, dC + (size_t)q0 * dldc * es,
+                                        (size_t)dldc * es, (size_t)m * es, (size_t)nq, st.s_out);
+            if (e) { dl_err = e; return; }
+          }
+        });
+      }
+      { std::lock_guard<std::mutex> l(dl_mu); dl_ready = j + 1; }
+      dl_cv.notify_all();
+    } else {
+      B200_CUDA_TRY(cudaStreamWaitEvent(st.s_out, st.ev_comp[j], 0));
+      B200_CUDA_TRY(cudaMemcpy2DAsync((char*)c + (size_t)j0 * ldc * es, (size_t)ldc * es, dC + (size_t)j0 * dldc * es,
+                                      (size_t)dldc * es, (size_t)m * es, (size_t)nj, cudaMemcpyDeviceToHost, st.s_out));
+    }
     t_d2h += (uint64_t)m * nj * es;
+  }
+  if (dl_started) {
+    downloader.join();
+    dl_started = false;
+    if (dl_err) return dl_err;
   }
   B200_CUDA_TRY(cudaStreamSynchronize(st.s_out));
   B200_CUDA_TRY(cudaStreamSynchronize(st.s_comp));
