@@ -170,13 +170,23 @@ simt_gemm_kernel(int opa, int opb, int64_t m, int64_t n, int64_t k, T alpha, T b
     __syncthreads();
   }
 
-  // fused epilogue: C = alpha*acc + beta*C; beta == 0 never reads C (blas/level3_impl.h:64)
+  // fused epilogue: C = alpha*acc + beta*C; beta == 0 never reads C (blas/level3_impl.h:64).  Per column, all loads
+  // are issued before the first store: a load that follows a store through the same pointer cannot be hoisted by the
+  // compiler and every read-modify-write would pay a full memory round trip.
 #pragma unroll
   for (int cn = 0; cn < RN; ++cn)
 #pragma unroll
     for (int jn = 0; jn < VE; ++jn) {
       const int64_t gj = n0 + cn * 16 * VE + ty * VE + jn;
       if (gj >= n) continue;
+      T old[Cfg::TM];
+#pragma unroll
+      for (int cm = 0; cm < RM; ++cm)
+#pragma unroll
+        for (int im = 0; im < VE; ++im) {
+          const int64_t gi = m0 + cm * 16 * VE + tx * VE + im;
+          old[cm * VE + im] = (!beta_zero && gi < m) ? C[gi + gj * ldc] : S::zero();
+        }
 #pragma unroll
       for (int cm = 0; cm < RM; ++cm)
 #pragma unroll
@@ -184,9 +194,8 @@ simt_gemm_kernel(int opa, int opb, int64_t m, int64_t n, int64_t k, T alpha, T b
           const int64_t gi = m0 + cm * 16 * VE + tx * VE + im;
           if (gi >= m) continue;
           T r = S::mul(alpha, acc[cm * VE + im][cn * VE + jn]);
-          T* pc = C + gi + gj * ldc;
-          if (!beta_zero) S::fma(r, beta, *pc);
-          *pc = r;
+          if (!beta_zero) S::fma(r, beta, old[cm * VE + im]);
+          C[gi + gj * ldc] = r;
         }
     }
 }

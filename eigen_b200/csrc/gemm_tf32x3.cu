@@ -24,7 +24,10 @@ constexpr int TM = 128, TN = 256, TK = 32, UK = 8, NSTAGE = 2;
 constexpr int A_PLANE = TM * TK * 4, B_PLANE = TN * TK * 4;
 constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;  // 98304
 constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int THREADS = 192;
+constexpr int THREADS = 192;     // complex / 256-tile kernels: TMA warp, MMA warp, 4 drain warps
+// real kernel: warpgroup 0 = TMA warp + MMA warp (+ 2 idle warps, setmaxnreg.dec 40); warpgroups 1-2 = 8 drain warps,
+// two per TMEM lane quadrant (setmaxnreg.inc 232: 128 fp32 accumulators per thread stay in registers)
+constexpr int THREADS_R = 384;
 constexpr int TMEM_COLS = 512;
 
 // ---------------- PTX wrappers ------------------------------------------------------------------------------
@@ -87,6 +90,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ---------------- pack: split op(X) into K-major tf32 hi / lo panels -----------------------------------------
 // element (r, kk) of the logical R x K operand lives at src[r*sr + kk*sk]; exactly one of sr, sk is 1.
 __global__ void __launch_bounds__(256)
@@ -136,11 +149,12 @@ struct Tf32Params {
 };
 
 // The tensor core adds into the fp32 TMEM accumulator without round-to-nearest; over a long k the truncation
-// bias grows linearly (measured: gauge ratio 34 at k = 8192 for one uninterrupted chain).  The chain is therefore
-// cut every KCHUNK_DEFAULT*32 k values: the epilogue warps fold each partial sum into C with IEEE fp32 adds
-// (C = alpha*acc + beta*C for the first chunk, C += alpha*acc afterwards) while the next chunk accumulates in the
-// other TMEM buffer.  Same idea as the reference's kc blocking, where every kc block ends in one FMA into C
-// (GeneralBlockPanelKernel.h:1025-1066).
+// bias grows linearly with the chain length (measured, profiles/accuracy_tf32x3_r01.md: relative Frobenius error
+// 15 eps per 256 k of uninterrupted chain, 963 eps and gauge ratio 54 at k = 16384).  The chain is therefore cut every
+// KCHUNK_DEFAULT*32 k values: drain warps pull each partial sum out of TMEM and add it with IEEE fp32 adds into
+// register accumulators while the next chunk accumulates in the other TMEM buffer -- the analogue of the reference's
+// kc blocking, where every kc block ends in one rounding into C (GeneralBlockPanelKernel.h:1025-1066), without
+// touching C more than once per tile.
 constexpr int KCHUNK_DEFAULT = 8;
 
 constexpr int GROUP = 16;  // tile rasterisation: a wave of 148 tiles covers ~16 x 9 tiles (2048 x 2304 of C): balanced A/B panel reuse in L2
@@ -154,7 +168,7 @@ __device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t ti
   tn = in / gsz;
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS_R, 1)
 tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
                    const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
                    const Tf32Params p) {
@@ -177,7 +191,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -192,6 +206,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
   const int64_t ntiles = p.tiles_m * p.tiles_n;
   const int nkb = (int)((p.k + TK - 1) / TK);
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     if (lane == 0) {  // ===== TMA producer =====
       int stage = 0;
@@ -246,42 +262,55 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
         }
       }
     }
+  }
   } else {
-    // ===== epilogue warps 2..5: TMEM -> registers -> C (alpha/beta fused) =====
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ===== drain warps 4..11: TMEM partial sums -> fp32 register accumulators -> C (alpha/beta fused) =====
+    // The tensor core adds into TMEM without round-to-nearest, so the chain is cut every kchunk k-blocks: each
+    // partial sum is pulled out with tcgen05.ld and added (IEEE fp32, round to nearest) into 128 register
+    // accumulators per thread while the next chunk accumulates in the other TMEM buffer.  C is touched once per tile.
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;    // which 128 of the 256 accumulator columns
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
-      const int64_t row = tm * TM + q * 32 + lane;
-      float* crow = p.C + row;
+      float accr[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) accr[j] = 0.f;
       for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
-        // first chunk: C = alpha*acc + beta*C (beta == 0: C is not read); later chunks: C += alpha*acc
-        const float beta = kb0 == 0 ? p.beta : 1.f;
-        const bool read_c = kb0 != 0 || !p.beta_zero;
         mbar_wait(tfull(acc), acc_phase);
         tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + (uint32_t)(acc * TN + c0) + ((uint32_t)(q * 32) << 16), r);
-          const int64_t col0 = tn * TN + c0;
-          if (row < p.m) {
-            // all loads of the 32 columns first, then all stores: a load placed after a store through the same
-            // pointer cannot be hoisted by the compiler, which would serialise 32 memory round trips
-            float old[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) old[j] = (read_c && col0 + j < p.n) ? crow[(col0 + j) * p.ldc] : 0.f;
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + (uint32_t)(acc * TN + half * 128 + c0) + ((uint32_t)(q * 32) << 16), r);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.n) crow[(col0 + j) * p.ldc] = fmaf(beta, old[j], p.alpha * __uint_as_float(r[j]));
-          }
+          for (int j = 0; j < 16; ++j) accr[c0 + j] += __uint_as_float(r[j]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      const int64_t row = tm * TM + q * 32 + lane;
+      if (row < p.m) {
+        const int64_t colbase = tn * TN + half * 128;
+        float* pc = p.C + row + colbase * p.ldc;
+        const int ncol = p.n - colbase > 128 ? 128 : (int)(p.n - colbase);   // valid columns of this half (may be <= 0)
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 8) {
+          // loads of 8 columns first, then their stores: a load placed after a store through the same pointer
+          // cannot be hoisted by the compiler, which would serialise every memory round trip
+          float old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) old[j] = (!p.beta_zero && c0 + j < ncol) ? pc[(int64_t)j * p.ldc] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < ncol) pc[(int64_t)j * p.ldc] = fmaf(p.beta, old[j], p.alpha * accr[c0 + j]);
+          pc += 8 * p.ldc;
+        }
       }
     }
   }
@@ -614,51 +643,57 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
       }
     }
   } else {
+    // drain warps: partial Re / Im sums -> 64 + 64 fp32 register accumulators (IEEE adds), C touched once per tile
     const int q = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
-      const int64_t row = tm * TM + q * 32 + lane;
-      float2* crow = p.C + row;
+      float are[CTN], aim[CTN];
+#pragma unroll
+      for (int j = 0; j < CTN; ++j) { are[j] = 0.f; aim[j] = 0.f; }
       for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
-        const float2 beta = kb0 == 0 ? p.beta : make_float2(1.f, 0.f);
-        const bool read_c = kb0 != 0 || !p.beta_zero;
         mbar_wait(tfull(acc), acc_phase);
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < CTN; c0 += 32) {
-          uint32_t re[32], im[32];
+          uint32_t r[32];
           const uint32_t t0 = tmem_base + (uint32_t)(acc * 2 * CTN + c0) + ((uint32_t)(q * 32) << 16);
-          tmem_ld32(t0, re);
-          tmem_ld32(t0 + CTN, im);
-          const int64_t col0 = tn * CTN + c0;
-          if (row < p.m) {
-            // loads first, stores afterwards (see the real kernel); 16 columns at a time to bound registers
+          tmem_ld32(t0, r);
 #pragma unroll
-            for (int h = 0; h < 32; h += 16) {
-              float2 old[16];
+          for (int j = 0; j < 32; ++j) are[c0 + j] += __uint_as_float(r[j]);
+          tmem_ld32(t0 + CTN, r);
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                old[j] = (read_c && col0 + h + j < p.n) ? crow[(col0 + h + j) * p.ldc] : make_float2(0.f, 0.f);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                if (col0 + h + j < p.n) {
-                  const float xr = __uint_as_float(re[h + j]), xi = __uint_as_float(im[h + j]);
-                  float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
-                  v.x += fmaf(beta.x, old[j].x, -beta.y * old[j].y);
-                  v.y += fmaf(beta.x, old[j].y, beta.y * old[j].x);
-                  crow[(col0 + h + j) * p.ldc] = v;
-                }
-              }
-            }
-          }
+          for (int j = 0; j < 32; ++j) aim[c0 + j] += __uint_as_float(r[j]);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      const int64_t row = tm * TM + q * 32 + lane;
+      if (row < p.m) {
+        float2* crow = p.C + row;
+        const int64_t colbase = tn * CTN;
+#pragma unroll
+        for (int c0 = 0; c0 < CTN; c0 += 8) {
+          // loads first, stores afterwards (a load behind a store to the same array cannot be hoisted)
+          float2 old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            old[j] = (!p.beta_zero && colbase + c0 + j < p.n) ? crow[(colbase + c0 + j) * p.ldc] : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (colbase + c0 + j < p.n) {
+              const float xr = are[c0 + j], xi = aim[c0 + j];
+              float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
+              v.x += fmaf(p.beta.x, old[j].x, -p.beta.y * old[j].y);
+              v.y += fmaf(p.beta.x, old[j].y, p.beta.y * old[j].x);
+              crow[(colbase + c0 + j) * p.ldc] = v;
+            }
+          }
+        }
       }
     }
   }
@@ -892,7 +927,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
   const int64_t ntiles = prm.tiles_m * prm.tiles_n;
   const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());  // persistent: one CTA per SM
   note_variant("tf32x3_tcgen05_128x256x32");
-  tf32x3_gemm_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, prm);
+  tf32x3_gemm_kernel<<<grid, THREADS_R, SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, prm);
   count_launch();
   return (int)cudaGetLastError();
 }
