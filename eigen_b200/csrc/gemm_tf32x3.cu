@@ -155,7 +155,7 @@ struct Tf32Params {
 // register accumulators while the next chunk accumulates in the other TMEM buffer -- the analogue of the reference's
 // kc blocking, where every kc block ends in one rounding into C (GeneralBlockPanelKernel.h:1025-1066), without
 // touching C more than once per tile.
-constexpr int KCHUNK_DEFAULT = 8;
+constexpr int KCHUNK_DEFAULT = 4;
 
 constexpr int GROUP = 16;  // tile rasterisation: a wave of 148 tiles covers ~16 x 9 tiles (2048 x 2304 of C): balanced A/B panel reuse in L2
 __device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t tiles_n, int64_t& tm, int64_t& tn) {
