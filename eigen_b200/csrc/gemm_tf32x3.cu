@@ -473,6 +473,193 @@ tf32x3_gemm256_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_co
   }
 }
 
+// ---------------- CTA-pair variant (cta_group::2): 256x256 tile per pair, half the B reads per SM --------------------
+// The single-CTA kernel is limited by the shared-memory port: every SS-mode tcgen05.mma re-reads A (4 KB) and B (8 KB)
+// from shared memory (96 B/clk) on top of the TMA fill (64 B/clk) against 128 B/clk.  A CTA pair (two SMs of one TPC)
+// multiplies a 256x256 tile with M=256 MMAs issued by the leader CTA: each CTA stages its own 128 rows of A and only ITS
+// half (128 rows) of B^T, the tensor cores exchange the B halves, so per SM the MMA reads 8 KB per instruction
+// (64 B/clk) and the TMA fill is 64 KB per 1536 clk (42 B/clk): 106 B/clk.  Three 64 KB stages fit.
+constexpr int P_STAGE_BYTES = 4 * A_PLANE;   // A_hi, A_lo, B_hi(half), B_lo(half): 4 x 16 KB
+constexpr int P_NSTAGE = 3;
+constexpr int P_SMEM_BYTES = P_NSTAGE * P_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // shared::cluster address of the same offset in the pair's leader (even) CTA
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive (once the MMAs issued so far are done) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS_R, 1)
+tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_constant__ CUtensorMap mapAl,
+                        const __grid_constant__ CUtensorMap mapBh, const __grid_constant__ CUtensorMap mapBl,
+                        const Tf32Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + P_NSTAGE * P_STAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (P_NSTAGE + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * P_NSTAGE + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * P_NSTAGE + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * P_NSTAGE + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapAl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBh)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapBl)) : "memory");
+    for (int s = 0; s < P_NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 16); }  // 8 drain warps x 2 CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int64_t ntiles = p.tiles_m * p.tiles_n;   // 256 x 256 tiles
+  const int nkb = (int)((p.k + TK - 1) / TK);
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      if (lane == 0) {  // ===== TMA producer (both CTAs; completion is counted on the LEADER's full barrier) =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+          int64_t tm, tn;
+          tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+          const int row_a = (int)(tm * 256 + rank * 128), row_b = (int)(tn * 256 + rank * 128);
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(empty(stage), phase ^ 1u);
+            if (leader) mbar_expect_tx(full(stage), 2 * P_STAGE_BYTES);
+            const uint32_t s0 = base + stage * P_STAGE_BYTES;
+            const uint32_t lbar = full(stage) & PEER_MASK;
+            tma_load_2d_pair(s0, &mapAh, kb * TK, row_a, lbar);
+            tma_load_2d_pair(s0 + A_PLANE, &mapAl, kb * TK, row_a, lbar);
+            tma_load_2d_pair(s0 + 2 * A_PLANE, &mapBh, kb * TK, row_b, lbar);
+            tma_load_2d_pair(s0 + 3 * A_PLANE, &mapBl, kb * TK, row_b, lbar);
+            if (++stage == P_NSTAGE) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      if (lane == 0) {  // ===== MMA issuer: leader CTA only, M = 256 across the pair =====
+        constexpr uint32_t idesc = umma_idesc_tf32(256, 256);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+          for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
+            mbar_wait(tempty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
+            const int kb1 = kb0 + p.kchunk < nkb ? kb0 + p.kchunk : nkb;
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(full(stage), phase);
+              tc_fence_after();
+              const uint32_t s0 = base + stage * P_STAGE_BYTES;
+              const uint64_t a_hi = umma_desc_sw128(s0), a_lo = umma_desc_sw128(s0 + A_PLANE);
+              const uint64_t b_hi = umma_desc_sw128(s0 + 2 * A_PLANE), b_lo = umma_desc_sw128(s0 + 3 * A_PLANE);
+#pragma unroll
+              for (int k8 = 0; k8 < TK / UK; ++k8) {
+                const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);
+                tc_mma_tf32_pair(d_tmem, a_lo + off, b_hi + off, idesc, ((kb - kb0) | k8) != 0);
+                tc_mma_tf32_pair(d_tmem, a_hi + off, b_lo + off, idesc, 1u);
+                tc_mma_tf32_pair(d_tmem, a_hi + off, b_hi + off, idesc, 1u);
+              }
+              tc_commit_pair(empty(stage));   // frees this stage in BOTH CTAs
+              if (++stage == P_NSTAGE) { stage = 0; phase ^= 1u; }
+            }
+            tc_commit_pair(tfull(acc));       // partial sum complete in both CTAs' TMEM
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ===== drain warps (both CTAs): own 128 rows of the pair tile; tempty is counted on the leader's barrier =====
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+      int64_t tm, tn;
+      tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+      float accr[128];
+#pragma unroll
+      for (int j = 0; j < 128; ++j) accr[j] = 0.f;
+      for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
+        mbar_wait(tfull(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tmem_base + (uint32_t)(acc * TN + half * 128 + c0) + ((uint32_t)(q * 32) << 16), r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) accr[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty(acc) & PEER_MASK);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      const int64_t row = tm * 256 + rank * 128 + q * 32 + lane;
+      if (row < p.m) {
+        const int64_t colbase = tn * TN + half * 128;
+        float* pc = p.C + row + colbase * p.ldc;
+        const int ncol = p.n - colbase > 128 ? 128 : (int)(p.n - colbase);
+#pragma unroll
+        for (int c0 = 0; c0 < 128; c0 += 8) {
+          float old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) old[j] = (!p.beta_zero && c0 + j < ncol) ? pc[(int64_t)j * p.ldc] : 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c0 + j < ncol) pc[(int64_t)j * p.ldc] = fmaf(p.beta, old[j], p.alpha * accr[c0 + j]);
+          pc += 8 * p.ldc;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------- complex<float>: same machinery on de-interleaved planes ---------------------------------------
 // C = A*B with A = Ar + i Ai, B = Br + i Bi:  Re = Ar.Br - Ai.Bi,  Im = Ar.Bi + Ai.Br  (the four real products of
 // the reference's complex gebp, GeneralBlockPanelKernel.h:566-744), each as a 3xTF32 product; the minus sign is the
@@ -905,6 +1092,33 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     const unsigned g2 = (unsigned)(nt < sm_count() ? nt : sm_count());
     note_variant("tf32x3_tcgen05_256x256x16");
     tf32x3_gemm256_kernel<<<g2, THREADS, SMEM2_BYTES, s>>>(mAh, mAl, mBh, mBl, prm);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
+  static const int use_pair = [] { const char* e = getenv("B200BLAS_TF32_PAIR"); return e ? atoi(e) : 0; }();
+  if (use_pair) {
+    // CTA pairs: every CTA loads 128-row boxes of A and of B^T
+    CUtensorMap mAh, mAl, mBh, mBl;
+    if (make_map(&mAh, Ah, p.m, p.k, Kp, 128) || make_map(&mAl, Al, p.m, p.k, Kp, 128) ||
+        make_map(&mBh, Bh, p.n, p.k, Kp, 128) || make_map(&mBl, Bl, p.n, p.k, Kp, 128))
+      return (int)cudaErrorInvalidValue;
+    Tf32Params prm;
+    prm.m = p.m; prm.n = p.n; prm.k = p.k;
+    prm.C = (float*)p.C; prm.ldc = p.ldc;
+    prm.alpha = (float)p.alpha[0]; prm.beta = (float)p.beta[0];
+    prm.beta_zero = (p.beta[0] == 0.0);
+    prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + 255) / 256;
+    prm.kchunk = kchunk_blocks();
+    static bool attrp_done = false;
+    if (!attrp_done) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+      attrp_done = true;
+    }
+    const int64_t nt = prm.tiles_m * prm.tiles_n;
+    int64_t pairs = sm_count() / 2;
+    if (nt < pairs) pairs = nt;
+    note_variant("tf32x3_tcgen05_pair_256x256x32");
+    tf32x3_gemm_pair_kernel<<<(unsigned)(2 * pairs), THREADS_R, P_SMEM_BYTES, s>>>(mAh, mAl, mBh, mBl, prm);
     count_launch();
     return (int)cudaGetLastError();
   }
