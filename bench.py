@@ -58,6 +58,12 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.mark_at = 0
+
+    def mark(self):
+        """Call at the start of the timed region: only samples taken after this point are reported (the sampler is
+        started before the warm-up because nvidia-smi needs ~0.3 s to deliver its first line)."""
+        self.mark_at = len(self.lines)
 
     def start(self):
         try:
@@ -83,7 +89,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        timed = self.lines[self.mark_at:]
+        window = "timed region"
+        if not timed:   # region shorter than one sampling period: fall back to the warm-up samples (same load)
+            timed, window = self.lines, "warm-up + timed region"
+        for ln in timed:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -101,7 +111,7 @@ class ClockSampler:
         busy = [s for s, p in zip(sm, power) if p > 0.5 * max(power)] or sm
         busy.sort()
         return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm), "sm_mhz_min": sm_sorted[0]}
+                "power_w_max": max(power), "samples": len(sm), "sm_mhz_min": sm_sorted[0], "window": window}
 
 
 def cpu_reference_leg(t, m, n, k, alpha, beta, steps, warmup, slab_cols):
@@ -233,10 +243,11 @@ def run_ours(args):
             r = eigen_b200.gemm_dev(t, "N", "N", m, n, k, alpha, A, m, B, k, beta, Cd, m, stream=stream.cuda_stream)
             assert r == 0, eigen_b200.last_error()
 
+        clocks.start()
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize()
-        clocks.start()
+        clocks.mark()
         launches0 = eigen_b200.kernel_launches()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
         ev[0].record(stream)
@@ -338,12 +349,13 @@ def run_ours(args):
             Cd = torch.ones(n, m, dtype=dt, device="cuda")
         else:
             A = B = Cd = None
+        clocks.start()
         for _ in range(args.warmup):
             job.run(A, B, Cd)
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        clocks.start()
+        clocks.mark()
         launches0 = eigen_b200.kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

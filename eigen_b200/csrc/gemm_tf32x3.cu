@@ -1095,7 +1095,11 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     count_launch();
     return (int)cudaGetLastError();
   }
-  static const int use_pair = [] { const char* e = getenv("B200BLAS_TF32_PAIR"); return e ? atoi(e) : 0; }();
+  // CTA pairs win once there are enough 256x256 tiles to occupy the 74 pairs (profiles/variant_sweep_r01.md:
+  // 8192^3 276 vs 252 TF, 2048^3 162 vs 147 TF); B200BLAS_TF32_PAIR=0/1 forces the choice
+  static const int force_pair = [] { const char* e = getenv("B200BLAS_TF32_PAIR"); return e ? atoi(e) : -1; }();
+  const int64_t tiles256 = ((p.m + 255) / 256) * ((p.n + 255) / 256);
+  const bool use_pair = force_pair >= 0 ? force_pair != 0 : (p.m >= 512 && p.n >= 512 && tiles256 >= 32);
   if (use_pair) {
     // CTA pairs: every CTA loads 128-row boxes of A and of B^T
     CUtensorMap mAh, mAl, mBh, mBl;
