@@ -892,6 +892,189 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
   }
 }
 
+// ---------------- complex CTA-pair variant: 256 x 128 complex tile per pair ------------------------------------------
+// Same pairing as tf32x3_gemm_pair_kernel.  Per CTA and stage: 4 A planes of 128 rows (64 KB) + 4 B planes of 64 rows
+// (32 KB), two stages.  M = 256, N = 128 MMAs; TMEM per buffer: Re (128 columns) | Im (128 columns), double buffered.
+constexpr int CP_BN = 128;                                   // complex columns per pair tile
+constexpr int CP_BPLANE = (CP_BN / 2) * TK * 4;              // 8192: this CTA's half of one B plane
+constexpr int CP_STAGE_BYTES = 4 * A_PLANE + 4 * CP_BPLANE;  // 98304
+constexpr int CP_SMEM_BYTES = NSTAGE * CP_STAGE_BYTES + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS_R, 1)
+tf32x3_cgemm_pair_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t bars = base + NSTAGE * CP_STAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (NSTAGE + s); };
+  auto tfull = [&](int a) { return bars + 8u * (2 * NSTAGE + a); };
+  auto tempty = [&](int a) { return bars + 8u * (2 * NSTAGE + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * NSTAGE + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.a[i])) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&maps.b[i])) : "memory");
+    }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 16); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int64_t ntiles = p.tiles_m * p.tiles_n;   // 256 x 128 complex tiles
+  const int nkb = (int)((p.k + TK - 1) / TK);
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      if (lane == 0) {  // ===== TMA producer =====
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+          int64_t tm, tn;
+          tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+          const int row_a = (int)(tm * 256 + rank * 128), row_b = (int)(tn * CP_BN + rank * (CP_BN / 2));
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(empty(stage), phase ^ 1u);
+            if (leader) mbar_expect_tx(full(stage), 2 * CP_STAGE_BYTES);
+            const uint32_t s0 = base + stage * CP_STAGE_BYTES;
+            const uint32_t lbar = full(stage) & PEER_MASK;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tma_load_2d_pair(s0 + i * A_PLANE, &maps.a[i], kb * TK, row_a, lbar);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tma_load_2d_pair(s0 + 4 * A_PLANE + i * CP_BPLANE, &maps.b[i], kb * TK, row_b, lbar);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      if (lane == 0) {  // ===== MMA issuer (leader CTA) =====
+        constexpr uint32_t idesc = umma_idesc_tf32(256, CP_BN);
+        constexpr uint32_t idesc_neg = idesc | (1u << 13);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+          for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
+            mbar_wait(tempty(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_re = tmem_base + (uint32_t)(acc * 2 * CP_BN), d_im = d_re + CP_BN;
+            const int kb1 = kb0 + p.kchunk < nkb ? kb0 + p.kchunk : nkb;
+            for (int kb = kb0; kb < kb1; ++kb) {
+              mbar_wait(full(stage), phase);
+              tc_fence_after();
+              const uint32_t s0 = base + stage * CP_STAGE_BYTES;
+              uint64_t a[4], b[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { a[i] = umma_desc_sw128(s0 + i * A_PLANE); b[i] = umma_desc_sw128(s0 + 4 * A_PLANE + i * CP_BPLANE); }
+#pragma unroll
+              for (int k8 = 0; k8 < TK / UK; ++k8) {
+                const uint64_t off = (uint64_t)((k8 * UK * 4) >> 4);
+                const uint32_t first = ((kb - kb0) | k8) != 0;
+                tc_mma_tf32_pair(d_re, a[1] + off, b[0] + off, idesc, first);
+                tc_mma_tf32_pair(d_re, a[0] + off, b[1] + off, idesc, 1u);
+                tc_mma_tf32_pair(d_re, a[0] + off, b[0] + off, idesc, 1u);
+                tc_mma_tf32_pair(d_re, a[3] + off, b[2] + off, idesc_neg, 1u);
+                tc_mma_tf32_pair(d_re, a[2] + off, b[3] + off, idesc_neg, 1u);
+                tc_mma_tf32_pair(d_re, a[2] + off, b[2] + off, idesc_neg, 1u);
+                tc_mma_tf32_pair(d_im, a[1] + off, b[2] + off, idesc, first);
+                tc_mma_tf32_pair(d_im, a[0] + off, b[3] + off, idesc, 1u);
+                tc_mma_tf32_pair(d_im, a[0] + off, b[2] + off, idesc, 1u);
+                tc_mma_tf32_pair(d_im, a[3] + off, b[0] + off, idesc, 1u);
+                tc_mma_tf32_pair(d_im, a[2] + off, b[1] + off, idesc, 1u);
+                tc_mma_tf32_pair(d_im, a[2] + off, b[0] + off, idesc, 1u);
+              }
+              tc_commit_pair(empty(stage));
+              if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
+            }
+            tc_commit_pair(tfull(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // drain warps: quadrant q, column half h -> Re[h*64, +64) and Im[h*64, +64) of this CTA's 128 rows
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+      int64_t tm, tn;
+      tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+      float are[64], aim[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) { are[j] = 0.f; aim[j] = 0.f; }
+      for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
+        mbar_wait(tfull(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16];
+          const uint32_t t0 = tmem_base + (uint32_t)(acc * 2 * CP_BN + half * 64 + c0) + ((uint32_t)(q * 32) << 16);
+          tmem_ld16(t0, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) are[c0 + j] += __uint_as_float(r[j]);
+          tmem_ld16(t0 + CP_BN, r);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) aim[c0 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty(acc) & PEER_MASK);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      const int64_t row = tm * 256 + rank * 128 + q * 32 + lane;
+      if (row < p.m) {
+        const int64_t colbase = tn * CP_BN + half * 64;
+        float2* pc = p.C + row + colbase * p.ldc;
+        const int ncol = p.n - colbase > 64 ? 64 : (int)(p.n - colbase);
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 8) {
+          float2 old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) old[j] = (!p.beta_zero && c0 + j < ncol) ? pc[(int64_t)j * p.ldc] : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (c0 + j < ncol) {
+              const float xr = are[c0 + j], xi = aim[c0 + j];
+              float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
+              v.x += fmaf(p.beta.x, old[j].x, -p.beta.y * old[j].y);
+              v.y += fmaf(p.beta.x, old[j].y, p.beta.y * old[j].x);
+              pc[(int64_t)j * p.ldc] = v;
+            }
+          }
+          pc += 8 * p.ldc;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------- TF32 pipe peak: back-to-back M=128 N=256 K=8 MMAs on zeroed shared memory ---------------------
 __global__ void __launch_bounds__(128, 1) tf32_peak_kernel(int iters, float* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1020,6 +1203,34 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
     count_launch();
   }
   B200_CUDA_TRY(cudaGetLastError());
+  static const int force_pair = [] { const char* e = getenv("B200BLAS_TF32_PAIR"); return e ? atoi(e) : -1; }();
+  const int64_t ptiles = ((p.m + 255) / 256) * ((p.n + CP_BN - 1) / CP_BN);
+  const bool use_pair = force_pair >= 0 ? force_pair != 0 : (p.m >= 512 && p.n >= 256 && ptiles >= 32);
+  if (use_pair) {
+    CMaps maps;
+    for (int i = 0; i < 4; ++i) {
+      if (make_map(&maps.a[i], ap[i], p.m, p.k, Kp, 128) || make_map(&maps.b[i], bp[i], p.n, p.k, Kp, CP_BN / 2)) return (int)cudaErrorInvalidValue;
+    }
+    CTf32Params prm;
+    prm.m = p.m; prm.n = p.n; prm.k = p.k;
+    prm.C = (float2*)p.C; prm.ldc = p.ldc;
+    prm.alpha = make_float2((float)p.alpha[0], (float)p.alpha[1]);
+    prm.beta = make_float2((float)p.beta[0], (float)p.beta[1]);
+    prm.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
+    prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + CP_BN - 1) / CP_BN;
+    prm.kchunk = kchunk_blocks();
+    static bool attrcp_done = false;
+    if (!attrcp_done) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES));
+      attrcp_done = true;
+    }
+    int64_t pairs = sm_count() / 2;
+    if (ptiles < pairs) pairs = ptiles;
+    note_variant("tf32x3_tcgen05_c_pair_256x128x32");
+    tf32x3_cgemm_pair_kernel<<<(unsigned)(2 * pairs), THREADS_R, CP_SMEM_BYTES, s>>>(maps, prm);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   CMaps maps;
   for (int i = 0; i < 4; ++i) {
     if (make_map(&maps.a[i], ap[i], p.m, p.k, Kp, TM) || make_map(&maps.b[i], bp[i], p.n, p.k, Kp, CTN)) return (int)cudaErrorInvalidValue;
