@@ -191,3 +191,50 @@ def test_lu_trailing_update_shape(L):
     assert np.array_equal(M[:bs], M0[:bs]) and np.array_equal(M[:, :bs], M0[:, :bs])
     ref, g = oa.hp_gemm("d", "N", "N", mm, mm, bs, -1.0, M0[bs:, :bs], N, M0[:bs, bs:], N, 1.0, M0[bs:, bs:], N)
     assert (np.abs(M[bs:, bs:] - ref) / (oa.EPS["d"] * g)).max() < 16.0
+
+
+def test_concurrent_callers_are_safe(L):
+    """The reference's ?gemm_ is re-entrant and Eigen may call it from many user threads: four threads
+    issue host-pointer products of different types and shapes at once (ctypes releases the GIL); every result must
+    equal the single-threaded one bit for bit."""
+    import threading
+    rng = np.random.default_rng(99)
+    jobs = []
+    for i, (t, m, n, k) in enumerate([("d", 700, 650, 900), ("s", 1100, 900, 1300), ("z", 300, 420, 510), ("c", 640, 512, 768),
+                                      ("d", 129, 1031, 77), ("s", 333, 222, 111)]):
+        A = oa.rand_matrix(rng, t, m, k)
+        B = oa.rand_matrix(rng, t, k, n)
+        C0 = oa.rand_matrix(rng, t, m, n)
+        want = C0.copy(order="F")
+        assert oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "N", m, n, k, 1.0, A, m, B, k, 1.0, want, m) == 0
+        jobs.append((t, m, n, k, A, B, C0, want))
+    errors = []
+
+    def worker(idx):
+        for rep in range(3):
+            t, m, n, k, A, B, C0, want = jobs[(idx + rep) % len(jobs)]
+            c = C0.copy(order="F")
+            r = oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "N", m, n, k, 1.0, A, m, B, k, 1.0, c, m)
+            if r != 0 or c.tobytes() != want.tobytes():
+                errors.append((idx, rep, t, r))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+
+def test_pageable_large_operands_go_through_the_staging_ring(L):
+    """Ordinary malloc'ed (pageable) matrices above the ring threshold: same result as the oracle, padding intact."""
+    rng = np.random.default_rng(5)
+    m, n, k = 1500, 1100, 1300          # every operand > 4 MiB -> pinned ring + copy workers + downloader thread
+    for t in "ds":
+        A = oa.rand_matrix(rng, t, m, k, ld=m + 5)
+        B = oa.rand_matrix(rng, t, k, n, ld=k + 3)
+        C0 = oa.rand_matrix(rng, t, m, n, ld=m + 7)
+        c = C0.copy(order="F")
+        assert oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "T" if False else "N", m, n, k, 0.7, A, m + 5, B, k + 3, 1.3, c, m + 7) == 0
+        assert c[m:].tobytes() == C0[m:].tobytes()
+        _check(t, "N", "N", m, n, k, 0.7, 1.3, A, B, C0, c, m + 7, port_too=False)
