@@ -422,12 +422,37 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
   // loader modes: 16-byte copies need the tile dimension contiguous, a 16-byte aligned base and (real) an even ld
   const int amode = !a.dim_contig ? LD_K : (a.vec16 ? LD_DIM16 : LD_DIM8);
   const int bmode = !b.dim_contig ? LD_K : (b.vec16 ? LD_DIM16 : LD_DIM8);
-  if (use_mbar()) {
-    note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta_mbar" : "dmma_d_128x64x16_w32x32_2cta_mbar");
-    return launch_modes<CfgM>(cplx, amode, bmode, p, s, a, b, ep);
+  // k-slicing: one wave of 296 CTAs streams (16*128 + 18.5*64) panel rows x k x 8 bytes; beyond ~4096 k that window no
+  // longer fits the 126 MB L2 and panel reuse between CTAs depends on them staying in lockstep (measured at 16384^3:
+  // L2 hit rate 83 % -> 53 % and 82 -> 338 GB of DRAM reads once the CTAs drift).  Large-k products therefore run as
+  // consecutive k-slices (beta = 1 after the first), which is also the reference's kc blocking
+  // (GeneralMatrixMatrix.h:172-174): every slice ends in one rounding into C.
+  static const int64_t kslice_env = [] { const char* e = getenv("B200BLAS_DMMA_KSLICE"); return e ? (int64_t)atoll(e) : (int64_t)-1; }();
+  const int64_t sc = cplx ? 2 : 1;
+  int64_t kslice = kslice_env >= 0 ? kslice_env : 4096 / sc;
+  const bool big_panels = (double)(p.m + p.n) * sc > 6000.0;   // small m+n: the panels of all tiles fit L2 anyway
+  if (kslice <= 0 || !big_panels || p.k < 2 * kslice) kslice = p.k;
+  const int64_t nslices = (p.k + kslice / 2) / kslice > 0 ? (p.k + kslice / 2) / kslice : 1;   // nearest count
+  const int64_t slice_len = ((p.k + nslices - 1) / nslices + 15) / 16 * 16;                   // equal slices, BK-aligned
+  for (int64_t k0 = 0; k0 < p.k; k0 += slice_len) {
+    GemmProblem q = p;
+    q.k = p.k - k0 < slice_len ? p.k - k0 : slice_len;
+    PanelSrc a2 = a, b2 = b;
+    a2.base = a.base + sc * (a.dim_contig ? k0 * p.lda : k0);
+    b2.base = b.base + sc * (b.dim_contig ? k0 * p.ldb : k0);
+    EpiParams e2 = ep;
+    if (k0 > 0) { e2.beta[0] = 1.0; e2.beta[1] = 0.0; e2.beta_zero = 0; }
+    int rc;
+    if (use_mbar()) {
+      note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta_mbar" : "dmma_d_128x64x16_w32x32_2cta_mbar");
+      rc = launch_modes<CfgM>(cplx, amode, bmode, q, s, a2, b2, e2);
+    } else {
+      note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta" : "dmma_d_128x64x16_w32x32_2cta");
+      rc = launch_modes<CfgB>(cplx, amode, bmode, q, s, a2, b2, e2);
+    }
+    if (rc) return rc;
   }
-  note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta" : "dmma_d_128x64x16_w32x32_2cta");
-  return launch_modes<CfgB>(cplx, amode, bmode, p, s, a, b, ep);
+  return 0;
 }
 
 }  // namespace b200
