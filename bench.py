@@ -279,15 +279,18 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                traffic = json.load(open(tp)).get("dram_bytes_per_step")
             except Exception:
                 traffic = None
+        per_step = max(1, launches // max(args.steps, 1))
         result["roofline"] = {
             "bound": "tensor", "achieved": issued / (avg_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
             "frac": issued / (avg_ms * 1e-3) / 1e12 / peak if peak > 0 else None, "traffic": traffic,
-            "kernel": variant, "launch_ms_avg": avg_ms, "launch_ms_best": kern_ms,
-            "algorithmic_flops_per_launch": flops, "tensor_pipe_flops_per_launch": issued,
-            "algorithmic_bytes_per_launch": ESIZE[t] * (m * k + k * n + 2 * m * n), "peak_source": peak_src,
+            "kernel": variant, "step_ms_avg": avg_ms, "step_ms_best": kern_ms, "launches_per_step": per_step,
+            "note": "one step = one product = %d launch(es) of the kernel (k-slices / pack + product); achieved, traffic "
+                    "and the algorithmic figures are per step" % per_step,
+            "algorithmic_flops_per_step": flops, "tensor_pipe_flops_per_step": issued,
+            "algorithmic_bytes_per_step": ESIZE[t] * (m * k + k * n + 2 * m * n), "peak_source": peak_src,
         }
         # ---- e2e: the drop-in F77 entry point with HOST operands --------------------------------------------
         del A, B, Cd

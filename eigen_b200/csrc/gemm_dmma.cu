@@ -425,11 +425,13 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
   // k-slicing: one wave of 296 CTAs streams (16*128 + 18.5*64) panel rows x k x 8 bytes; beyond ~4096 k that window no
   // longer fits the 126 MB L2 and panel reuse between CTAs depends on them staying in lockstep (measured at 16384^3:
   // L2 hit rate 83 % -> 53 % and 82 -> 338 GB of DRAM reads once the CTAs drift).  Large-k products therefore run as
-  // consecutive k-slices (beta = 1 after the first), which is also the reference's kc blocking
-  // (GeneralMatrixMatrix.h:172-174): every slice ends in one rounding into C.
+  // consecutive k-slices of 2048 (beta = 1 after the first), which is also the reference's kc blocking
+  // (GeneralMatrixMatrix.h:172-174): every slice ends in one rounding into C.  Measured at 16384^3
+  // (profiles/variant_sweep_r01.md): unsliced 265.5 ms / 340 GB of DRAM traffic, 4096-slices 266.8 ms / 102 GB,
+  // 2048-slices 268.1 ms / 57.6 GB (L2 hit rate 92 %).
   static const int64_t kslice_env = [] { const char* e = getenv("B200BLAS_DMMA_KSLICE"); return e ? (int64_t)atoll(e) : (int64_t)-1; }();
   const int64_t sc = cplx ? 2 : 1;
-  int64_t kslice = kslice_env >= 0 ? kslice_env : 4096 / sc;
+  int64_t kslice = kslice_env >= 0 ? kslice_env : 2048;
   const bool big_panels = (double)(p.m + p.n) * sc > 6000.0;   // small m+n: the panels of all tiles fit L2 anyway
   if (kslice <= 0 || !big_panels || p.k < 2 * kslice) kslice = p.k;
   const int64_t nslices = (p.k + kslice / 2) / kslice > 0 ? (p.k + kslice / 2) / kslice : 1;   // nearest count
