@@ -29,7 +29,6 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
 size_t tf32x3_workspace_bytes(const GemmProblem& p);
 bool dmma_supported(const GemmProblem& p);
 bool tf32x3_supported(const GemmProblem& p);
-int launch_scale_c(const GemmProblem& p, cudaStream_t s);   // C = beta*C only (k == 0)
 double pipe_peak(int pipe, int millis);
 
 void count_launch(int n = 1);

@@ -355,11 +355,7 @@ int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const Pa
   const int64_t tiles_m = (p.m * sc + C::BM - 1) / C::BM, tiles_n = (p.n * sc + C::BN - 1) / C::BN;
   const int64_t tiles = tiles_m * tiles_n;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(dmma_gemm_kernel<C, CPLX, AMODE, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
-  }
+  B200_CUDA_TRY(cudaFuncSetAttribute(dmma_gemm_kernel<C, CPLX, AMODE, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));   // per device and cheap: set on every launch
   dmma_gemm_kernel<C, CPLX, AMODE, BMODE><<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(
       a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep, tiles_m, tiles_n);
   count_launch();

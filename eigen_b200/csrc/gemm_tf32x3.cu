@@ -1219,11 +1219,7 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
     prm.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
     prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + CP_BN - 1) / CP_BN;
     prm.kchunk = kchunk_blocks();
-    static bool attrcp_done = false;
-    if (!attrcp_done) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES));
-      attrcp_done = true;
-    }
+    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES));
     int64_t pairs = sm_count() / 2;
     if (ptiles < pairs) pairs = ptiles;
     note_variant("tf32x3_tcgen05_c_pair_256x128x32");
@@ -1243,11 +1239,7 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
   prm.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + CTN - 1) / CTN;
   prm.kchunk = kchunk_blocks();
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM_BYTES));
-    attr_done = true;
-  }
+  B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM_BYTES));   // per device and cheap: set on every launch
   const int64_t ntiles = prm.tiles_m * prm.tiles_n;
   const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
   note_variant("tf32x3_tcgen05_c_128x64x32");
@@ -1294,11 +1286,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     prm.beta_zero = (p.beta[0] == 0.0);
     prm.tiles_m = (p.m + TM2 - 1) / TM2; prm.tiles_n = (p.n + TN - 1) / TN;
     prm.kchunk = 1 << 30;
-    static bool attr2_done = false;
-    if (!attr2_done) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      attr2_done = true;
-    }
+    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     const int64_t nt = prm.tiles_m * prm.tiles_n;
     const unsigned g2 = (unsigned)(nt < sm_count() ? nt : sm_count());
     note_variant("tf32x3_tcgen05_256x256x16");
@@ -1324,11 +1312,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     prm.beta_zero = (p.beta[0] == 0.0);
     prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + 255) / 256;
     prm.kchunk = kchunk_blocks();
-    static bool attrp_done = false;
-    if (!attrp_done) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-      attrp_done = true;
-    }
+    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     const int64_t nt = prm.tiles_m * prm.tiles_n;
     int64_t pairs = sm_count() / 2;
     if (nt < pairs) pairs = nt;
@@ -1348,11 +1332,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
   prm.beta_zero = (p.beta[0] == 0.0);
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + TN - 1) / TN;
   prm.kchunk = kchunk_blocks();
-  static bool attr_done = false;
-  if (!attr_done) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));   // per device and cheap: set on every launch
   const int64_t ntiles = prm.tiles_m * prm.tiles_n;
   const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());  // persistent: one CTA per SM
   note_variant("tf32x3_tcgen05_128x256x32");

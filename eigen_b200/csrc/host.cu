@@ -278,12 +278,10 @@ struct PinnedRing {
     // software pipeline over the ring: DMA of chunk i+1 runs while the workers copy chunk i out
     size_t issued = 0, retired = 0;
     const size_t nchunks = (ncols + cols_per - 1) / cols_per;
-    int slots[NBUF];
     while (retired < nchunks) {
       while (issued < nchunks && issued - retired < (size_t)NBUF) {
         const size_t c0 = issued * cols_per, nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
         const int slot = (int)(issued % NBUF);
-        slots[slot] = slot;
         B200_CUDA_TRY(cudaMemcpy2DAsync(buf[slot], width, src + c0 * spitch, spitch, width, nc, cudaMemcpyDeviceToHost, s));
         B200_CUDA_TRY(cudaEventRecord(free_ev[slot], s));
         used[slot] = false;
@@ -295,7 +293,6 @@ struct PinnedRing {
       copy_pool().copy2d(dst + c0 * dpitch, dpitch, buf[slot], width, width, nc);
       ++retired;
     }
-    (void)slots;
     return 0;
   }
 };
