@@ -52,6 +52,15 @@ __device__ __forceinline__ void cp_async_zfill(void* smem_dst, const void* gmem_
   else
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES), "r"(src_bytes));
 }
+// plain cp.async of BYTES bytes (no source-size operand: ptxas turns a variable source size into ~6 extra instructions)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_full(void* smem_dst, const void* gmem_src) {
+  static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
+  if constexpr (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src));
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }

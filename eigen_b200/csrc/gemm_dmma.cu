@@ -19,6 +19,7 @@
 // profiles/variant_sweep_r01.md over 128x128/1-CTA, 128x64/2-CTA, 16-warp and BK=32 variants).  The loader mode of
 // each operand (16-byte / 8-byte / transposed) is a template parameter so that no mode state occupies registers.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -96,19 +97,30 @@ struct Loader {
         if (dim0 + r0 + (int64_t)e * RSTEP < s.dim) vmask |= 1u << e;
     }
   }
-  __device__ __forceinline__ int64_t estep(const PanelSrc& s) const {
+  __device__ __forceinline__ int64_t estep(const PanelSrc& s) const {   // doubles between consecutive copies
     return DIMC ? (int64_t)KKSTEP * s.ld * RS : (int64_t)RSTEP * s.ld * RS;
   }
-  __device__ __forceinline__ const double* tile_ptr(const PanelSrc& s, int64_t kt) const {
-    return p + kt * (DIMC ? (int64_t)BK * s.ld * RS : (int64_t)BK * RS);
+  __device__ __forceinline__ int64_t kstep(const PanelSrc& s) const {   // doubles between consecutive k-tiles
+    return DIMC ? (int64_t)BK * s.ld * RS : (int64_t)BK * RS;
   }
-  // issue copy e of one k-tile: ptile = tile_ptr(kt), krem = k - k0 clamped to int (ragged last tile)
-  __device__ __forceinline__ void copy(double* S, const PanelSrc& s, int e, const double* ptile, int krem) const {
+  // Copy e of an interior k-tile (all BK k values exist): q = source of THIS copy (the caller advances it by estep).
+  // Rows / columns outside the matrix are simply not loaded: whatever the slot holds only ever reaches rows / columns
+  // of C that the epilogue masks (every output element is its own dot product).
+  __device__ __forceinline__ void copy_fast(double* S, const double* q, int e) const {
+    double* dst = S + soff + e * SSTEP;
+    if constexpr (DIMC) {
+      if (vmask == (uint32_t)BYTES) cp_async_full<BYTES>(dst, q);
+      else if (vmask) cp_async_zfill<BYTES>(dst, q, (int)vmask);   // odd last row of a 16-byte real granule
+    } else {
+      if ((vmask >> e) & 1u) cp_async_full<BYTES>(dst, q);
+    }
+  }
+  // Copy e of the ragged last k-tile: k values beyond the matrix must read as zero (they reach every output)
+  __device__ __forceinline__ void copy_ragged(double* S, const double* q, const double* fallback, int e, int krem) const {
     int nbytes;
     if constexpr (DIMC) nbytes = (kk0 + e * KKSTEP < krem) ? (int)vmask : 0;
     else nbytes = (((vmask >> e) & 1u) && kk0 < krem) ? BYTES : 0;
-    const double* src = nbytes ? ptile + (int64_t)e * estep(s) : s.base;
-    cp_async_zfill<BYTES>(S + soff + e * SSTEP, src, nbytes);
+    cp_async_zfill<BYTES>(S + soff + e * SSTEP, nbytes ? q : fallback, nbytes);
   }
 };
 
@@ -128,6 +140,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(done) : "r"(a), "r"(parity) : "memory");
   } while (!done);
 }
+// one non-blocking probe: 1 if the phase with the given parity has completed
+__device__ __forceinline__ uint32_t mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return done;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -140,6 +159,7 @@ struct EpiParams {
   double alpha[2], beta[2];
   int beta_zero;
   int conja, conjb;
+  int diag;   // B200BLAS_DMMA_DIAG (measurement only, results are garbage): 1 = no copies, no waits; 2 = copies, no waits
 };
 
 // grouped tile order: consecutive CTAs walk GROUP tile-rows first so that one wave of CTAs shares a compact
@@ -186,17 +206,30 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
     for (int j = 0; j < NJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
   const int64_t nkt = (k + BK - 1) / BK;
+  // running source pointers: pa_next / pb_next = copy 0 of the next tile to be loaded; the per-copy and per-tile strides
+  // are loop invariant (no 64-bit multiplies in the loop)
+  const int64_t ea = la.estep(a), eb = lb.estep(b), ka = la.kstep(a), kb = lb.kstep(b);
+  const double* pa_next = la.p;
+  const double* pb_next = lb.p;
   auto load_all = [&](int64_t kt) {
     double* sa = As + (kt % STAGES) * C::PANEL_A;
     double* sb = Bs + (kt % STAGES) * C::PANEL_B;
     const int64_t rem = k - kt * BK;
-    const int krem = rem > (1 << 20) ? (1 << 20) : (int)rem;
-    const double* pa = la.tile_ptr(a, kt);
-    const double* pb = lb.tile_ptr(b, kt);
+    const double* qa = pa_next;
+    const double* qb = pb_next;
+    if (rem >= BK) {
 #pragma unroll
-    for (int e = 0; e < LA::E; ++e) la.copy(sa, a, e, pa, krem);
+      for (int e = 0; e < LA::E; ++e) { la.copy_fast(sa, qa, e); qa += ea; }
 #pragma unroll
-    for (int e = 0; e < LB::E; ++e) lb.copy(sb, b, e, pb, krem);
+      for (int e = 0; e < LB::E; ++e) { lb.copy_fast(sb, qb, e); qb += eb; }
+    } else {
+#pragma unroll
+      for (int e = 0; e < LA::E; ++e) { la.copy_ragged(sa, qa, a.base, e, (int)rem); qa += ea; }
+#pragma unroll
+      for (int e = 0; e < LB::E; ++e) { lb.copy_ragged(sb, qb, b.base, e, (int)rem); qb += eb; }
+    }
+    pa_next += ka;
+    pb_next += kb;
   };
   constexpr int LOOK = C::MBAR ? STAGES - 2 : STAGES - 1;   // tiles in flight ahead of the one being multiplied
   __shared__ uint64_t full_bar[C::MBAR ? STAGES : 1], empty_bar[C::MBAR ? STAGES : 1];
@@ -217,14 +250,20 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
   }
 
   const int fr = lane >> 2, fk = lane & 3;  // fragment row (0..7) and k (0..3) of this lane
+  // The barrier probes for tile kt+1 are issued BEFORE the last 16 DMMAs of tile kt and only checked after them, so
+  // the ~100-cycle mbarrier round trip is hidden under MMA issue instead of stalling every warp at each tile boundary
+  // (measured: main loop without copies/waits 35.9 TFLOP/s, with blocking waits at the boundary 32.6).
+  uint32_t pre_full = 0, pre_empty = 0;
   for (int64_t kt = 0; kt < nkt; ++kt) {
     const int64_t nxt = kt + LOOK;
-    const bool do_load = nxt < nkt;
+    const bool do_load = nxt < nkt && ep.diag != 1;
     const int st = (int)(kt % STAGES), sn = (int)(nxt % STAGES);
     if constexpr (C::MBAR) {
       // the ring slot of tile nxt was last read by tile nxt - STAGES: every warp must have released it
-      if (do_load && nxt >= STAGES) mbar_wait(&empty_bar[sn], (uint32_t)((nxt / STAGES - 1) & 1));
-      mbar_wait(&full_bar[st], (uint32_t)((kt / STAGES) & 1));
+      if (!ep.diag) {
+        if (do_load && nxt >= STAGES && !pre_empty) mbar_wait(&empty_bar[sn], (uint32_t)((nxt / STAGES - 1) & 1));
+        if (!pre_full) mbar_wait(&full_bar[st], (uint32_t)((kt / STAGES) & 1));
+      }
     } else {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
@@ -232,35 +271,64 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
     double* sa_n = As + sn * C::PANEL_A;
     double* sb_n = Bs + sn * C::PANEL_B;
     const int64_t rem_n = k - nxt * BK;
-    const int krem_n = rem_n > (1 << 20) ? (1 << 20) : (int)rem_n;
-    const double* pa_n = la.tile_ptr(a, nxt);
-    const double* pb_n = lb.tile_ptr(b, nxt);
+    const bool fast = rem_n >= BK;   // interior tile: unpredicated-size copies
+    const double* qa = pa_next;
+    const double* qb = pb_next;
     const double* As_ = As + st * C::PANEL_A + wm * C::WM + fr;
     const double* Bs_ = Bs + st * C::PANEL_B + wn * C::WN + fr;
+    // MODE 0: no copies ride along (tail of the k loop / diagnostic); 1: interior tile (plain copies); 2: ragged last tile
+    auto tile_body = [&](auto mode_tag) {
+      constexpr int MODE = decltype(mode_tag)::value;
 #pragma unroll
-    for (int k4 = 0; k4 < BK / 4; ++k4) {
-      double af[MI], bf[NJ];
+      for (int k4 = 0; k4 < BK / 4; ++k4) {
+        double af[MI], bf[NJ];
 #pragma unroll
-      for (int i = 0; i < MI; ++i) af[i] = As_[(k4 * 4 + fk) * C::LDA_S + i * 8];
+        for (int i = 0; i < MI; ++i) af[i] = As_[(k4 * 4 + fk) * C::LDA_S + i * 8];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) bf[j] = Bs_[(k4 * 4 + fk) * C::LDB_S + j * 8];
-      // a quarter of the next tile's copies rides along with each k4 step
-      if (do_load) {
+        for (int j = 0; j < NJ; ++j) bf[j] = Bs_[(k4 * 4 + fk) * C::LDB_S + j * 8];
+        // a quarter of the next tile's copies rides along with each k4 step
+        if constexpr (MODE != 0) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          if ((e % (BK / 4)) == k4) {
-            if (e < LA::E) la.copy(sa_n, a, e, pa_n, krem_n);
-            if (e < LB::E) lb.copy(sb_n, b, e, pb_n, krem_n);
+          // copies are issued in increasing e (the source pointers are running sums): k4 step j takes the j-th chunk
+          constexpr int PER_A = (LA::E + BK / 4 - 1) / (BK / 4), PER_B = (LB::E + BK / 4 - 1) / (BK / 4);
+#pragma unroll
+          for (int e = 0; e < LA::E; ++e) {
+            if (e / PER_A == k4) {
+              if constexpr (MODE == 1) la.copy_fast(sa_n, qa, e); else la.copy_ragged(sa_n, qa, a.base, e, (int)rem_n);
+              qa += ea;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < LB::E; ++e) {
+            if (e / PER_B == k4) {
+              if constexpr (MODE == 1) lb.copy_fast(sb_n, qb, e); else lb.copy_ragged(sb_n, qb, b.base, e, (int)rem_n);
+              qb += eb;
+            }
           }
         }
+        if constexpr (C::MBAR) {
+          if (k4 == BK / 4 - 1) {
+            // this thread's copies of tile nxt are all issued: publish them, then probe the barriers of tile kt+1
+            if (MODE != 0) cp_async_mbar_arrive(&full_bar[sn]);
+            pre_full = pre_empty = 0;
+            if (!ep.diag && kt + 1 < nkt) {
+              pre_full = mbar_try(&full_bar[(kt + 1) % STAGES], (uint32_t)(((kt + 1) / STAGES) & 1));
+              const int64_t n2 = nxt + 1;
+              if (n2 < nkt && n2 >= STAGES) pre_empty = mbar_try(&empty_bar[n2 % STAGES], (uint32_t)((n2 / STAGES - 1) & 1));
+            }
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
       }
-#pragma unroll
-      for (int i = 0; i < MI; ++i)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-    }
+    };
+    if (!do_load) tile_body(std::integral_constant<int, 0>{});
+    else if (fast) tile_body(std::integral_constant<int, 1>{});
+    else tile_body(std::integral_constant<int, 2>{});
+    if (do_load) { pa_next += ka; pb_next += kb; }
     if constexpr (C::MBAR) {
-      if (do_load) cp_async_mbar_arrive(&full_bar[sn]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[st]);   // this warp has read everything it needs from slot st
     } else {
@@ -415,6 +483,8 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
   ep.beta[0] = p.beta[0]; ep.beta[1] = p.beta[1];
   ep.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
   ep.conja = (p.opa == OP_C); ep.conjb = (p.opb == OP_C);
+  static const int diag_env = [] { const char* e = getenv("B200BLAS_DMMA_DIAG"); return e ? atoi(e) : 0; }();
+  ep.diag = diag_env;
   // loader modes: 16-byte copies need the tile dimension contiguous, a 16-byte aligned base and (real) an even ld
   const int amode = !a.dim_contig ? LD_K : (a.vec16 ? LD_DIM16 : LD_DIM8);
   const int bmode = !b.dim_contig ? LD_K : (b.vec16 ? LD_DIM16 : LD_DIM8);

@@ -107,6 +107,13 @@ double pipe_peak(int pipe, int millis) {
     r = time_loop([&] { ffma_peak_kernel<<<blocks, threads>>>((float*)out, iters); count_launch(); }, flops, millis);
   } else if (pipe == 3) {
     r = tf32_pipe_peak(millis);
+  } else if (pipe == 10 || pipe == 11 || pipe == 12) {
+    // occupancy sensitivity of the DMMA pipe: 16 / 8 / 4 warps per SM (4 / 2 / 1 per sub-partition), 16 independent tiles each
+    const int iters = 4096;
+    const int nb = pipe == 10 ? sms * 2 : pipe == 11 ? sms : sms;
+    const int nt = pipe == 12 ? 128 : 256;
+    const double flops = (double)nb * (nt / 32) * iters * 16.0 * 512.0;
+    r = time_loop([&] { dmma_peak_kernel<<<nb, nt>>>((double*)out, iters); count_launch(); }, flops, millis);
   }
   cudaFree(out);
   return r;
