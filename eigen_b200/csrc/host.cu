@@ -527,7 +527,14 @@ static int gemm_entry(int type, const char* ta, const char* tb, const int* pm, c
   load_scalar(type, pbeta, beta);
   t_error[0] = 0;
   int err;
-  if (is_device_ptr(c)) {
+  const bool dev_c = is_device_ptr(c);
+  if (*pk > 0 && (is_device_ptr(a) != dev_c || is_device_ptr(b) != dev_c)) {
+    // mixed residency (some operands in host memory, some on the device) is not a BLAS calling convention
+    snprintf(t_error, sizeof t_error, "operands must be all host or all device pointers");
+    info = -1;
+    return xerbla_(k_names[type], &info, 6);
+  }
+  if (dev_c) {
     GemmProblem p;
     p.type = type; p.opa = opa; p.opb = opb; p.m = *pm; p.n = *pn; p.k = *pk;
     p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = beta[0]; p.beta[1] = beta[1];
