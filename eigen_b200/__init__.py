@@ -19,7 +19,7 @@ TYPE_CODE = {"s": 0, "d": 1, "c": 2, "z": 3}
 VARIANT = {"auto": 0, "simt": 1, "dmma": 2, "tf32x3": 3}
 
 # every symbol include/b200blas.h declares
-EXPORTS = ["sgemm_", "dgemm_", "cgemm_", "zgemm_", "xerbla_", "b200blas_gemm_dev", "b200blas_version",
+EXPORTS = ["sgemm_", "dgemm_", "cgemm_", "zgemm_", "ssyrk_", "dsyrk_", "csyrk_", "zsyrk_", "cherk_", "zherk_", "xerbla_", "b200blas_gemm_dev", "b200blas_version",
            "b200blas_device_ok", "b200blas_last_error", "b200blas_last_variant", "b200blas_kernel_launches",
            "b200blas_set_variant", "b200blas_last_transfer", "b200blas_release", "b200blas_pipe_peak"]
 
@@ -58,6 +58,10 @@ def lib():
     for name in ("sgemm_", "dgemm_", "cgemm_", "zgemm_"):
         f = getattr(L, name)
         f.argtypes = [cp, cp, ip, ip, ip, vp, vp, ip, vp, ip, vp, vp, ip]
+        f.restype = i
+    for name in ("ssyrk_", "dsyrk_", "csyrk_", "zsyrk_", "cherk_", "zherk_"):
+        f = getattr(L, name)
+        f.argtypes = [cp, cp, ip, ip, vp, vp, ip, vp, vp, ip]
         f.restype = i
     L.b200blas_gemm_dev.argtypes = [i, C.c_char, C.c_char, i, i, i, vp, vp, C.c_int64, vp, C.c_int64, vp, vp,
                                     C.c_int64, vp, i]

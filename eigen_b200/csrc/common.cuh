@@ -18,7 +18,19 @@ struct GemmProblem {
   const void* A; int64_t lda;
   const void* B; int64_t ldb;
   void* C; int64_t ldc;
+  // rank-k updates (?syrk_/?herk_, blas/level3_impl.h:357-433,564-627) run on the same kernels with a triangular mask:
+  int uplo = 0;   // 0: whole m x n window; UPLO_UPPER / UPLO_LOWER: only that triangle of C is read and written
+  int herm = 0;   // 1: Hermitian update -- the imaginary part of the diagonal is stored as exactly zero
 };
+enum : int { UPLO_FULL = 0, UPLO_UPPER = 1, UPLO_LOWER = 2 };
+// element (i, j) belongs to the referenced triangle
+__host__ __device__ __forceinline__ bool in_triangle(int uplo, int64_t i, int64_t j) {
+  return uplo == UPLO_FULL || (uplo == UPLO_UPPER ? i <= j : i >= j);
+}
+// the tile [i0, i1) x [j0, j1) has no element in the referenced triangle
+__host__ __device__ __forceinline__ bool tile_outside(int uplo, int64_t i0, int64_t i1, int64_t j0, int64_t j1) {
+  return uplo == UPLO_UPPER ? (i0 > j1 - 1) : uplo == UPLO_LOWER ? (i1 - 1 < j0) : false;
+}
 
 static inline int type_bytes(int t) { return t == TY_S ? 4 : t == TY_Z ? 16 : 8; }
 

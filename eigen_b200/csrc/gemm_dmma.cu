@@ -159,6 +159,7 @@ struct EpiParams {
   double alpha[2], beta[2];
   int beta_zero;
   int conja, conjb;
+  int uplo, herm;   // triangular mask of ?syrk_/?herk_ (common.cuh)
   int diag;   // B200BLAS_DMMA_DIAG (measurement only, results are garbage): 1 = no copies, no waits; 2 = copies, no waits
 };
 
@@ -190,6 +191,7 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
   tile_of(blockIdx.x, tiles_m, tiles_n, tm, tn);
   constexpr int SC = CPLX ? 2 : 1;  // real rows/cols per scalar
   const int64_t m0 = tm * (C::BM / SC), n0 = tn * (C::BN / SC);  // tile origin in scalars
+  if (tile_outside(ep.uplo, m0, m0 + C::BM / SC, n0, n0 + C::BN / SC)) return;   // rank-k update: other triangle
 
   constexpr int BK = C::BK, STAGES = C::STAGES;
   using LA = Loader<C::BM, C::THREADS, CPLX, BK, AMODE, C::LDA_S>;
@@ -352,7 +354,7 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
           const int64_t gi = m0 + wm * C::WM + i * 8 + fr;
-          old[c][i] = (!ep.beta_zero && gi < m && gj < n) ? Cmat[gi + gj * ldc] : 0.0;
+          old[c][i] = (!ep.beta_zero && gi < m && gj < n && in_triangle(ep.uplo, gi, gj)) ? Cmat[gi + gj * ldc] : 0.0;
         }
       }
 #pragma unroll
@@ -361,7 +363,7 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
           const int64_t gi = m0 + wm * C::WM + i * 8 + fr;
-          if (gi < m && gj < n) Cmat[gi + gj * ldc] = fma(beta, old[c][i], alpha * acc[i][j][c]);
+          if (gi < m && gj < n && in_triangle(ep.uplo, gi, gj)) Cmat[gi + gj * ldc] = fma(beta, old[c][i], alpha * acc[i][j][c]);
         }
       }
     }
@@ -393,7 +395,7 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
           const int64_t gi = m0 + wm * (C::WM / 2) + i * 4 + (fr >> 1);
-          const bool ok = gi < m && gj < n;
+          const bool ok = gi < m && gj < n && in_triangle(ep.uplo, gi, gj);
           cr[i] = ok ? Cmat[2 * (gi + gj * ldc)] : 0.0;
           ci[i] = ok ? Cmat[2 * (gi + gj * ldc) + 1] : 0.0;
         }
@@ -404,7 +406,8 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
 #pragma unroll
       for (int i = 0; i < MI; ++i) {
         const int64_t gi = m0 + wm * (C::WM / 2) + i * 4 + (fr >> 1);
-        if (gi < m && gj < n) Cmat[2 * (gi + gj * ldc) + (odd ? 1 : 0)] = outv[i];
+        if (gi < m && gj < n && in_triangle(ep.uplo, gi, gj))
+          Cmat[2 * (gi + gj * ldc) + (odd ? 1 : 0)] = (odd && ep.herm && gi == gj) ? 0.0 : outv[i];
       }
     }
   }
@@ -483,6 +486,7 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
   ep.beta[0] = p.beta[0]; ep.beta[1] = p.beta[1];
   ep.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
   ep.conja = (p.opa == OP_C); ep.conjb = (p.opb == OP_C);
+  ep.uplo = p.uplo; ep.herm = p.herm;
   static const int diag_env = [] { const char* e = getenv("B200BLAS_DMMA_DIAG"); return e ? atoi(e) : 0; }();
   ep.diag = diag_env;
   // loader modes: 16-byte copies need the tile dimension contiguous, a 16-byte aligned base and (real) an even ld

@@ -78,7 +78,7 @@ template <typename T, int RM, int RN, int BK>
 __global__ void __launch_bounds__(256)
 simt_gemm_kernel(int opa, int opb, int64_t m, int64_t n, int64_t k, T alpha, T beta, bool beta_zero,
                  const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb, T* __restrict__ C,
-                 int64_t ldc) {
+                 int64_t ldc, int uplo, int herm) {
   using Cfg = SimtCfg<T, RM, RN, BK>;
   using S = Sc<T>;
   constexpr int VE = Cfg::VE, BM = Cfg::BM, BN = Cfg::BN, LDSA = Cfg::LDSA, LDSB = Cfg::LDSB;
@@ -87,6 +87,7 @@ simt_gemm_kernel(int opa, int opb, int64_t m, int64_t n, int64_t k, T alpha, T b
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t m0 = (int64_t)blockIdx.x * BM, n0 = (int64_t)blockIdx.y * BN;
+  if (tile_outside(uplo, m0, m0 + BM, n0, n0 + BN)) return;   // rank-k update: tile entirely in the other triangle
 
   T acc[Cfg::TM][Cfg::TN];
 #pragma unroll
@@ -185,16 +186,17 @@ simt_gemm_kernel(int opa, int opb, int64_t m, int64_t n, int64_t k, T alpha, T b
 #pragma unroll
         for (int im = 0; im < VE; ++im) {
           const int64_t gi = m0 + cm * 16 * VE + tx * VE + im;
-          old[cm * VE + im] = (!beta_zero && gi < m) ? C[gi + gj * ldc] : S::zero();
+          old[cm * VE + im] = (!beta_zero && gi < m && in_triangle(uplo, gi, gj)) ? C[gi + gj * ldc] : S::zero();
         }
 #pragma unroll
       for (int cm = 0; cm < RM; ++cm)
 #pragma unroll
         for (int im = 0; im < VE; ++im) {
           const int64_t gi = m0 + cm * 16 * VE + tx * VE + im;
-          if (gi >= m) continue;
+          if (gi >= m || !in_triangle(uplo, gi, gj)) continue;
           T r = S::mul(alpha, acc[cm * VE + im][cn * VE + jn]);
           if (!beta_zero) S::fma(r, beta, old[cm * VE + im]);
+          if constexpr (sizeof(T) != sizeof(typename S::real)) { if (herm && gi == gj) r.y = 0; }
           C[gi + gj * ldc] = r;
         }
     }
@@ -221,7 +223,8 @@ int launch_t(const GemmProblem& p, cudaStream_t s) {
   }
   const bool beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
   simt_gemm_kernel<T, RM, RN, BK><<<grid, 256, 0, s>>>(p.opa, p.opb, p.m, p.n, p.k, alpha, beta, beta_zero,
-                                                       (const T*)p.A, p.lda, (const T*)p.B, p.ldb, (T*)p.C, p.ldc);
+                                                       (const T*)p.A, p.lda, (const T*)p.B, p.ldb, (T*)p.C, p.ldc,
+                                                       p.uplo, p.herm);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -146,6 +146,7 @@ struct Tf32Params {
   int beta_zero;
   int64_t tiles_m, tiles_n;
   int kchunk;  // k-blocks accumulated in TMEM before the partial sum is folded into C (see KCHUNK_DEFAULT)
+  int uplo;    // triangular mask of ?syrk_ (common.cuh)
 };
 
 // The tensor core adds into the fp32 TMEM accumulator without round-to-nearest; over a long k the truncation
@@ -215,6 +216,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int64_t tm, tn;
         tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * TM, tm * TM + TM, tn * TN, tn * TN + TN)) continue;   // rank-k update: other triangle
         const int row_a = (int)(tm * TM), row_b = (int)(tn * TN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty(stage), phase ^ 1u);
@@ -236,6 +238,9 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t tm, tn;
+        tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * TM, tm * TM + TM, tn * TN, tn * TN + TN)) continue;   // rank-k update: other triangle
         for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {   // one accumulation chunk per TMEM buffer
           mbar_wait(tempty(acc), acc_phase ^ 1u);
           tc_fence_after();
@@ -276,6 +281,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * TM, tm * TM + TM, tn * TN, tn * TN + TN)) continue;   // rank-k update: other triangle
       float accr[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) accr[j] = 0.f;
@@ -305,10 +311,12 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_const
           // cannot be hoisted by the compiler, which would serialise every memory round trip
           float old[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) old[j] = (!p.beta_zero && c0 + j < ncol) ? pc[(int64_t)j * p.ldc] : 0.f;
+          for (int j = 0; j < 8; ++j)
+            old[j] = (!p.beta_zero && c0 + j < ncol && in_triangle(p.uplo, row, colbase + c0 + j)) ? pc[(int64_t)j * p.ldc] : 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (c0 + j < ncol) pc[(int64_t)j * p.ldc] = fmaf(p.beta, old[j], p.alpha * accr[c0 + j]);
+            if (c0 + j < ncol && in_triangle(p.uplo, row, colbase + c0 + j))
+              pc[(int64_t)j * p.ldc] = fmaf(p.beta, old[j], p.alpha * accr[c0 + j]);
           pc += 8 * p.ldc;
         }
       }
@@ -557,6 +565,7 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         for (int64_t tile = pair; tile < ntiles; tile += npairs) {
           int64_t tm, tn;
           tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * 256, tm * 256 + 256, tn * 256, tn * 256 + 256)) continue;   // rank-k update: other triangle
           const int row_a = (int)(tm * 256 + rank * 128), row_b = (int)(tn * 256 + rank * 128);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(empty(stage), phase ^ 1u);
@@ -579,6 +588,9 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+          int64_t tm, tn;
+          tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+          if (tile_outside(p.uplo, tm * 256, tm * 256 + 256, tn * 256, tn * 256 + 256)) continue;   // rank-k update: other triangle
           for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
             mbar_wait(tempty(acc), acc_phase ^ 1u);
             tc_fence_after();
@@ -616,6 +628,7 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
     for (int64_t tile = pair; tile < ntiles; tile += npairs) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * 256, tm * 256 + 256, tn * 256, tn * 256 + 256)) continue;   // rank-k update: other triangle
       float accr[128];
 #pragma unroll
       for (int j = 0; j < 128; ++j) accr[j] = 0.f;
@@ -643,10 +656,12 @@ tf32x3_gemm_pair_kernel(const __grid_constant__ CUtensorMap mapAh, const __grid_
         for (int c0 = 0; c0 < 128; c0 += 8) {
           float old[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) old[j] = (!p.beta_zero && c0 + j < ncol) ? pc[(int64_t)j * p.ldc] : 0.f;
+          for (int j = 0; j < 8; ++j)
+            old[j] = (!p.beta_zero && c0 + j < ncol && in_triangle(p.uplo, row, colbase + c0 + j)) ? pc[(int64_t)j * p.ldc] : 0.f;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (c0 + j < ncol) pc[(int64_t)j * p.ldc] = fmaf(p.beta, old[j], p.alpha * accr[c0 + j]);
+            if (c0 + j < ncol && in_triangle(p.uplo, row, colbase + c0 + j))
+              pc[(int64_t)j * p.ldc] = fmaf(p.beta, old[j], p.alpha * accr[c0 + j]);
           pc += 8 * p.ldc;
         }
       }
@@ -722,6 +737,7 @@ struct CTf32Params {
   int beta_zero;
   int64_t tiles_m, tiles_n;
   int kchunk;
+  int uplo, herm;   // triangular mask of ?syrk_/?herk_; herm: imaginary part of the diagonal stored as zero
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -765,6 +781,7 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int64_t tm, tn;
         tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * TM, tm * TM + TM, tn * CTN, tn * CTN + CTN)) continue;   // rank-k update: other triangle
         const int row_a = (int)(tm * TM), row_b = (int)(tn * CTN);
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(empty(stage), phase ^ 1u);
@@ -787,6 +804,9 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int64_t tm, tn;
+        tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * TM, tm * TM + TM, tn * CTN, tn * CTN + CTN)) continue;   // rank-k update: other triangle
         for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
           mbar_wait(tempty(acc), acc_phase ^ 1u);
           tc_fence_after();
@@ -837,6 +857,7 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * TM, tm * TM + TM, tn * CTN, tn * CTN + CTN)) continue;   // rank-k update: other triangle
       float are[CTN], aim[CTN];
 #pragma unroll
       for (int j = 0; j < CTN; ++j) { are[j] = 0.f; aim[j] = 0.f; }
@@ -869,14 +890,16 @@ tf32x3_cgemm_kernel(const __grid_constant__ CMaps maps, const CTf32Params p) {
           float2 old[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            old[j] = (!p.beta_zero && colbase + c0 + j < p.n) ? crow[(colbase + c0 + j) * p.ldc] : make_float2(0.f, 0.f);
+            old[j] = (!p.beta_zero && colbase + c0 + j < p.n && in_triangle(p.uplo, row, colbase + c0 + j))
+                         ? crow[(colbase + c0 + j) * p.ldc] : make_float2(0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (colbase + c0 + j < p.n) {
+            if (colbase + c0 + j < p.n && in_triangle(p.uplo, row, colbase + c0 + j)) {
               const float xr = are[c0 + j], xi = aim[c0 + j];
               float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
               v.x += fmaf(p.beta.x, old[j].x, -p.beta.y * old[j].y);
               v.y += fmaf(p.beta.x, old[j].y, p.beta.y * old[j].x);
+              if (p.herm && row == colbase + c0 + j) v.y = 0.f;
               crow[(colbase + c0 + j) * p.ldc] = v;
             }
           }
@@ -949,6 +972,7 @@ tf32x3_cgemm_pair_kernel(const __grid_constant__ CMaps maps, const CTf32Params p
         for (int64_t tile = pair; tile < ntiles; tile += npairs) {
           int64_t tm, tn;
           tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * 256, tm * 256 + 256, tn * CP_BN, tn * CP_BN + CP_BN)) continue;   // rank-k update: other triangle
           const int row_a = (int)(tm * 256 + rank * 128), row_b = (int)(tn * CP_BN + rank * (CP_BN / 2));
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(empty(stage), phase ^ 1u);
@@ -972,6 +996,9 @@ tf32x3_cgemm_pair_kernel(const __grid_constant__ CMaps maps, const CTf32Params p
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t tile = pair; tile < ntiles; tile += npairs) {
+          int64_t tm, tn;
+          tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+          if (tile_outside(p.uplo, tm * 256, tm * 256 + 256, tn * CP_BN, tn * CP_BN + CP_BN)) continue;   // rank-k update: other triangle
           for (int kb0 = 0; kb0 < nkb; kb0 += p.kchunk) {
             mbar_wait(tempty(acc), acc_phase ^ 1u);
             tc_fence_after();
@@ -1020,6 +1047,7 @@ tf32x3_cgemm_pair_kernel(const __grid_constant__ CMaps maps, const CTf32Params p
     for (int64_t tile = pair; tile < ntiles; tile += npairs) {
       int64_t tm, tn;
       tile_of(tile, p.tiles_m, p.tiles_n, tm, tn);
+        if (tile_outside(p.uplo, tm * 256, tm * 256 + 256, tn * CP_BN, tn * CP_BN + CP_BN)) continue;   // rank-k update: other triangle
       float are[64], aim[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) { are[j] = 0.f; aim[j] = 0.f; }
@@ -1051,14 +1079,16 @@ tf32x3_cgemm_pair_kernel(const __grid_constant__ CMaps maps, const CTf32Params p
         for (int c0 = 0; c0 < 64; c0 += 8) {
           float2 old[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) old[j] = (!p.beta_zero && c0 + j < ncol) ? pc[(int64_t)j * p.ldc] : make_float2(0.f, 0.f);
+          for (int j = 0; j < 8; ++j)
+            old[j] = (!p.beta_zero && c0 + j < ncol && in_triangle(p.uplo, row, colbase + c0 + j)) ? pc[(int64_t)j * p.ldc] : make_float2(0.f, 0.f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (c0 + j < ncol) {
+            if (c0 + j < ncol && in_triangle(p.uplo, row, colbase + c0 + j)) {
               const float xr = are[c0 + j], xi = aim[c0 + j];
               float2 v = make_float2(fmaf(p.alpha.x, xr, -p.alpha.y * xi), fmaf(p.alpha.x, xi, p.alpha.y * xr));
               v.x += fmaf(p.beta.x, old[j].x, -p.beta.y * old[j].y);
               v.y += fmaf(p.beta.x, old[j].y, p.beta.y * old[j].x);
+              if (p.herm && row == colbase + c0 + j) v.y = 0.f;
               pc[(int64_t)j * p.ldc] = v;
             }
           }
@@ -1219,6 +1249,7 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
     prm.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
     prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + CP_BN - 1) / CP_BN;
     prm.kchunk = kchunk_blocks();
+    prm.uplo = p.uplo; prm.herm = p.herm;
     B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES));
     int64_t pairs = sm_count() / 2;
     if (ptiles < pairs) pairs = ptiles;
@@ -1239,6 +1270,7 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
   prm.beta_zero = (p.beta[0] == 0.0 && p.beta[1] == 0.0);
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + CTN - 1) / CTN;
   prm.kchunk = kchunk_blocks();
+    prm.uplo = p.uplo; prm.herm = p.herm;
   B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM_BYTES));   // per device and cheap: set on every launch
   const int64_t ntiles = prm.tiles_m * prm.tiles_n;
   const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
@@ -1273,7 +1305,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
   }
   B200_CUDA_TRY(cudaGetLastError());
   static const int force_tile = [] { const char* e = getenv("B200BLAS_TF32_TILE"); return e ? atoi(e) : 0; }();
-  const bool big = force_tile == 256;  // measured slower than the 128x256 kernel (profiles/variant_sweep_r01.md): opt-in only
+  const bool big = force_tile == 256 && p.uplo == 0;  // measured slower than the 128x256 kernel (profiles/variant_sweep_r01.md): opt-in only
   if (big) {
     CUtensorMap mAh, mAl, mBh, mBl;
     if (make_map(&mAh, Ah, p.m, p.k, Kp, 256, TK2) || make_map(&mAl, Al, p.m, p.k, Kp, 256, TK2) ||
@@ -1286,6 +1318,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     prm.beta_zero = (p.beta[0] == 0.0);
     prm.tiles_m = (p.m + TM2 - 1) / TM2; prm.tiles_n = (p.n + TN - 1) / TN;
     prm.kchunk = 1 << 30;
+    prm.uplo = 0;
     B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     const int64_t nt = prm.tiles_m * prm.tiles_n;
     const unsigned g2 = (unsigned)(nt < sm_count() ? nt : sm_count());
@@ -1312,6 +1345,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     prm.beta_zero = (p.beta[0] == 0.0);
     prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + 255) / 256;
     prm.kchunk = kchunk_blocks();
+    prm.uplo = p.uplo;
     B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     const int64_t nt = prm.tiles_m * prm.tiles_n;
     int64_t pairs = sm_count() / 2;
@@ -1332,6 +1366,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
   prm.beta_zero = (p.beta[0] == 0.0);
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + TN - 1) / TN;
   prm.kchunk = kchunk_blocks();
+    prm.uplo = p.uplo;
   B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));   // per device and cheap: set on every launch
   const int64_t ntiles = prm.tiles_m * prm.tiles_n;
   const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());  // persistent: one CTA per SM

@@ -226,6 +226,9 @@ static bool is_pageable(const void* p) {
   return at.type == cudaMemoryTypeUnregistered;
 }
 
+struct PinnedRing;
+static int ring_d2h_triangle(PinnedRing& ring, char* dst, size_t dpitch, const char* src, size_t spitch, size_t n, size_t es,
+                             int uplo, cudaStream_t s);
 struct PinnedRing {
   static constexpr int NBUF = 4;
   static constexpr size_t BYTES = (size_t)32 << 20;
@@ -296,6 +299,46 @@ struct PinnedRing {
     return 0;
   }
 };
+
+// device -> host for a rank-k update: whole columns travel into the pinned ring, but only the referenced triangle of
+// each column is copied into the caller's matrix (the other triangle is not referenced by ?syrk_/?herk_ and may be
+// in use by the caller).  Returns when the data is in place.
+static int ring_d2h_triangle(PinnedRing& ring, char* dst, size_t dpitch, const char* src, size_t spitch, size_t n, size_t es,
+                             int uplo, cudaStream_t s) {
+  if (n == 0) return 0;
+  const size_t width = n * es;
+  { const int e = ring.init(); if (e) return e; }
+  const size_t cols_per = width > PinnedRing::BYTES ? 0 : PinnedRing::BYTES / width;
+  if (cols_per == 0) {
+    // a single column exceeds a ring buffer (n > 4M doubles): copy the triangle column by column
+    for (size_t j = 0; j < n; ++j) {
+      const size_t lo = uplo == UPLO_UPPER ? 0 : j, hi = uplo == UPLO_UPPER ? j + 1 : n;
+      B200_CUDA_TRY(cudaMemcpyAsync(dst + j * dpitch + lo * es, src + j * spitch + lo * es, (hi - lo) * es, cudaMemcpyDeviceToHost, s));
+    }
+    return (int)cudaStreamSynchronize(s);
+  }
+  const size_t nchunks = (n + cols_per - 1) / cols_per;
+  size_t issued = 0, retired = 0;
+  while (retired < nchunks) {
+    while (issued < nchunks && issued - retired < (size_t)PinnedRing::NBUF) {
+      const size_t c0 = issued * cols_per, nc = n - c0 < cols_per ? n - c0 : cols_per;
+      const int slot = (int)(issued % PinnedRing::NBUF);
+      B200_CUDA_TRY(cudaMemcpy2DAsync(ring.buf[slot], width, src + c0 * spitch, spitch, width, nc, cudaMemcpyDeviceToHost, s));
+      B200_CUDA_TRY(cudaEventRecord(ring.free_ev[slot], s));
+      ++issued;
+    }
+    const size_t c0 = retired * cols_per, nc = n - c0 < cols_per ? n - c0 : cols_per;
+    const int slot = (int)(retired % PinnedRing::NBUF);
+    B200_CUDA_TRY(cudaEventSynchronize(ring.free_ev[slot]));
+    for (size_t jj = 0; jj < nc; ++jj) {
+      const size_t j = c0 + jj;
+      const size_t lo = uplo == UPLO_UPPER ? 0 : j, hi = uplo == UPLO_UPPER ? j + 1 : n;
+      memcpy(dst + j * dpitch + lo * es, ring.buf[slot] + jj * width + lo * es, (hi - lo) * es);
+    }
+    ++retired;
+  }
+  return 0;
+}
 
 // ---- per-process staging context ---------------------------------------------------------------------------
 struct Staging {
@@ -552,6 +595,100 @@ static int gemm_entry(int type, const char* ta, const char* tb, const int* pm, c
   return 0;
 }
 
+
+// ---- ?syrk_ / ?herk_: C.triangle = alpha*op(A)*op(A)^T|^H + beta*C.triangle -------------------------------
+// Reference: blas/level3_impl.h:357-433 (syrk) and :564-627 (herk).  The product runs on the GEMM kernels with
+// B := A and a triangular tile mask; only the referenced triangle of C is read or written.
+static const char* k_syrk_names[4] = {"SSYRK ", "DSYRK ", "CSYRK ", "ZSYRK "};
+static const char* k_herk_names[4] = {"", "", "CHERK ", "ZHERK "};
+
+static int run_host_rankk(const GemmProblem& hp) {
+  std::lock_guard<std::mutex> lock(g_stage.mu);
+  Staging& st = g_stage;
+  { const int e = st.init(); if (e) return e; }
+  const size_t es = (size_t)type_bytes(hp.type);
+  const int64_t n = hp.m, k = hp.k;
+  const bool beta_zero = (hp.beta[0] == 0.0 && hp.beta[1] == 0.0);
+  const int64_t ra = (hp.opa == OP_N) ? n : k, ca = (hp.opa == OP_N) ? k : n;
+  const int64_t q = 32 / (int64_t)es > 0 ? 32 / (int64_t)es : 1;
+  const int64_t dlda = round_up(std::max<int64_t>(ra, 1), q), dldc = round_up(n, q);
+  if (k > 0) { const int e = st.reserve(0, (size_t)dlda * (size_t)std::max<int64_t>(ca, 1) * es); if (e) return e; }
+  { const int e = st.reserve(2, (size_t)dldc * (size_t)n * es); if (e) return e; }
+  char* dA = (char*)st.dbuf[0];
+  char* dC = (char*)st.dbuf[2];
+  t_h2d = t_d2h = 0;
+  if (k > 0) {
+    const bool paged = (size_t)ra * ca * es >= ((size_t)4 << 20) && is_pageable(hp.A);
+    if (paged) { const int e = st.ring_in.h2d(dA, (size_t)dlda * es, (const char*)hp.A, (size_t)hp.lda * es, (size_t)ra * es, (size_t)ca, st.s_in); if (e) return e; }
+    else B200_CUDA_TRY(cudaMemcpy2DAsync(dA, (size_t)dlda * es, hp.A, (size_t)hp.lda * es, (size_t)ra * es, (size_t)ca, cudaMemcpyHostToDevice, st.s_in));
+    t_h2d += (uint64_t)ra * ca * es;
+  }
+  if (!beta_zero) {   // the whole window is uploaded (reading the other triangle is harmless); beta == 0: C is never read
+    const bool paged = (size_t)n * n * es >= ((size_t)4 << 20) && is_pageable(hp.C);
+    if (paged) { const int e = st.ring_in.h2d(dC, (size_t)dldc * es, (const char*)hp.C, (size_t)hp.ldc * es, (size_t)n * es, (size_t)n, st.s_in); if (e) return e; }
+    else B200_CUDA_TRY(cudaMemcpy2DAsync(dC, (size_t)dldc * es, hp.C, (size_t)hp.ldc * es, (size_t)n * es, (size_t)n, cudaMemcpyHostToDevice, st.s_in));
+    t_h2d += (uint64_t)n * n * es;
+  }
+  B200_CUDA_TRY(cudaEventRecord(st.ev_in[0], st.s_in));
+  B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_in[0], 0));
+  GemmProblem p = hp;
+  p.A = dA; p.lda = dlda; p.B = dA; p.ldb = dlda; p.C = dC; p.ldc = dldc;
+  { const int e = run_device(p, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
+  B200_CUDA_TRY(cudaStreamSynchronize(st.s_comp));
+  { const int e = ring_d2h_triangle(st.ring_out, (char*)hp.C, (size_t)hp.ldc * es, dC, (size_t)dldc * es, (size_t)n, es, hp.uplo, st.s_out); if (e) return e; }
+  t_d2h += (uint64_t)n * (n + 1) / 2 * es;
+  return 0;
+}
+
+static int rankk_entry(int type, bool herk, const char* uplo, const char* op, const int* pn, const int* pk, const void* palpha,
+                       const void* a, const int* plda, const void* pbeta, void* c, const int* pldc) {
+  const bool cplx = (type == TY_C || type == TY_Z);
+  const char* name = herk ? k_herk_names[type] : k_syrk_names[type];
+  const int ul = (*uplo == 'U' || *uplo == 'u') ? UPLO_UPPER : (*uplo == 'L' || *uplo == 'l') ? UPLO_LOWER : -1;
+  const int o = op_of(*op);
+  int info = 0;
+  if (ul < 0) info = 1;
+  else if (o == OP_INVALID || (!herk && cplx && o == OP_C) || (herk && o == OP_T)) info = 2;
+  else if (*pn < 0) info = 3;
+  else if (*pk < 0) info = 4;
+  else if (*plda < std::max(1, o == OP_N ? *pn : *pk)) info = 7;
+  else if (*pldc < std::max(1, *pn)) info = 10;
+  if (info) return xerbla_(name, &info, 6);
+  GemmProblem p;
+  p.type = type; p.m = *pn; p.n = *pn; p.k = *pk;
+  if (herk) {   // alpha and beta are REAL scalars (blas/level3_impl.h:585-586)
+    p.alpha[0] = (type == TY_C) ? (double)*(const float*)palpha : *(const double*)palpha; p.alpha[1] = 0.0;
+    p.beta[0] = (type == TY_C) ? (double)*(const float*)pbeta : *(const double*)pbeta; p.beta[1] = 0.0;
+  } else {
+    load_scalar(type, palpha, p.alpha);
+    load_scalar(type, pbeta, p.beta);
+  }
+  // op(A)*op(A)^T: 'N' -> A * A^T|^H, otherwise A^T|^H * A
+  const int tr = herk ? OP_C : OP_T;
+  if (o == OP_N) { p.opa = OP_N; p.opb = tr; } else { p.opa = tr; p.opb = OP_N; }
+  p.A = a; p.lda = *plda; p.B = a; p.ldb = *plda; p.C = c; p.ldc = *pldc;
+  p.uplo = ul; p.herm = herk ? 1 : 0;
+  if (*pn == 0) return 0;
+  const bool beta_one = (p.beta[0] == 1.0 && p.beta[1] == 0.0);
+  // syrk: no product when k == 0 (:397-398); herk: also when alpha == 0 (:617).  Then only the beta pass remains, and
+  // beta == 1 leaves C (including the imaginary part of a Hermitian diagonal) untouched.
+  const bool product = *pk > 0 && !(herk && p.alpha[0] == 0.0);
+  if (!product) {
+    if (beta_one) return 0;
+    p.k = 0;
+  }
+  t_error[0] = 0;
+  int err;
+  if (is_device_ptr(c)) {
+    err = run_device(p, nullptr, B200BLAS_AUTO);
+    if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
+  } else {
+    err = fail(run_host_rankk(p));
+  }
+  if (err) { info = -1; return xerbla_(name, &info, 6); }
+  return 0;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -581,6 +718,19 @@ int zgemm_(const char* ta, const char* tb, const int* m, const int* n, const int
            const int* ldc) {
   return gemm_entry(TY_Z, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }
+
+int ssyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
+           const float* beta, float* c, const int* ldc) { return rankk_entry(TY_S, false, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }
+int dsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda,
+           const double* beta, double* c, const int* ldc) { return rankk_entry(TY_D, false, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }
+int csyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
+           const float* beta, float* c, const int* ldc) { return rankk_entry(TY_C, false, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }
+int zsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda,
+           const double* beta, double* c, const int* ldc) { return rankk_entry(TY_Z, false, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }
+int cherk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
+           const float* beta, float* c, const int* ldc) { return rankk_entry(TY_C, true, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }
+int zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda,
+           const double* beta, double* c, const int* ldc) { return rankk_entry(TY_Z, true, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }
 
 int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, const void* alpha, const void* dA,
                       int64_t lda, const void* dB, int64_t ldb, const void* beta, void* dC, int64_t ldc, void* stream,

@@ -41,6 +41,22 @@ int cgemm_(const char* transa, const char* transb, const int* m, const int* n, c
 int zgemm_(const char* transa, const char* transb, const int* m, const int* n, const int* k, const double* alpha,
            const double* a, const int* lda, const double* b, const int* ldb, const double* beta, double* c,
            const int* ldc); /* replaces blas/complex_double.cpp via blas/level3_impl.h:12 */
+/* Rank-k updates, same kernels with a triangular tile mask.  Only the `uplo` triangle of C is read or
+ * written.  Semantics of blas/level3_impl.h:357-433 (syrk) and :564-627 (herk): info 1 bad uplo | 2 bad trans ('C' is
+ * invalid for csyrk_/zsyrk_, 'T' for ?herk_) | 3 n<0 | 4 k<0 | 7 lda<max(1,rows(A)) | 10 ldc<max(1,n); ?herk_ takes REAL
+ * alpha and beta and stores the imaginary part of the diagonal as exactly zero whenever it writes the diagonal. */
+int ssyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a,
+           const int* lda, const float* beta, float* c, const int* ldc);   /* blas/single.cpp via level3_impl.h:357 */
+int dsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a,
+           const int* lda, const double* beta, double* c, const int* ldc); /* blas/double.cpp via level3_impl.h:357 */
+int csyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a,
+           const int* lda, const float* beta, float* c, const int* ldc);   /* blas/complex_single.cpp via level3_impl.h:357 */
+int zsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a,
+           const int* lda, const double* beta, double* c, const int* ldc); /* blas/complex_double.cpp via level3_impl.h:357 */
+int cherk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a,
+           const int* lda, const float* beta, float* c, const int* ldc);   /* blas/complex_single.cpp via level3_impl.h:564 */
+int zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a,
+           const int* lda, const double* beta, double* c, const int* ldc); /* blas/complex_double.cpp via level3_impl.h:564 */
 /* Weak default prints "Eigen BLAS ERROR #<info>: <name>" like blas/xerbla.cpp:15-19; applications and testers
  * override it by defining their own xerbla_. */
 int xerbla_(const char* name, int* info, int len);

@@ -56,6 +56,19 @@ static int tester_xerbla(const char* name, int* info, int len) {
  * and the sm_100a library's) binds to the tester's version when liboracle.so is loaded RTLD_GLOBAL first */
 int xerbla_(const char* name, int* info, int len) { return tester_xerbla(name, info, len); }
 
+/* arm / disarm the tester's XERBLA from a test written in another language (used for the ?syrk_/?herk_ error exits,
+ * dblat3.f:2232-2296 DSYRK block of DCHKE): expect(name, infot) arms, result() returns 1 iff XERBLA was entered
+ * with that name and info since, and disarms. */
+void oracle_xerbla_expect(const char* name6, int infot) {
+  memcpy(g_srnamt, name6, 6); g_srnamt[6] = 0;
+  g_infot = infot; g_lerr = 0; g_ok = 1; g_armed = 1;
+}
+int oracle_xerbla_result(void) {
+  const int r = g_lerr && g_ok;
+  g_armed = 0;
+  return r;
+}
+
 /* ---- storage helpers: every matrix is kept as (re,im) double pairs; typed copies are made for the call ------ */
 typedef struct { int type, cplx, dbl; double eps; size_t esz; } tinfo;
 static tinfo make_tinfo(int type) {

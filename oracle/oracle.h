@@ -58,6 +58,16 @@ int oracle_zgemm_(const char* ta, const char* tb, const int* m, const int* n, co
 int oracle_gemm_omp(int type, char ta, char tb, int m, int n, int k, const void* alpha, const void* a, int lda,
                     const void* b, int ldb, const void* beta, void* c, int ldc, int threads);
 
+/* ---- rank-k updates, blas/level3_impl.h:357-433 (syrk), :564-627 (herk) -- oracle/rankk_port.c ---------------- */
+int oracle_ssyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* beta, float* c, const int* ldc);
+int oracle_dsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* beta, double* c, const int* ldc);
+int oracle_csyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* beta, float* c, const int* ldc);
+int oracle_zsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* beta, double* c, const int* ldc);
+int oracle_cherk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* beta, float* c, const int* ldc);
+int oracle_zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* beta, double* c, const int* ldc);
+void oracle_xerbla_expect(const char* name6, int infot);
+int oracle_xerbla_result(void);
+
 /* ---- high-precision reference (long double accumulate), column-at-a-time like DMMCH --------------------- */
 /* Computes rows listed in row_idx[nrows] (or all rows if row_idx==NULL) of C_ref = alpha*op(A)*op(B)+beta*C
  * into out (nrows x n, column-major, ld = nrows; ALWAYS double / double-complex, also for s and c) and the

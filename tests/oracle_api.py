@@ -24,6 +24,8 @@ _vp = C.c_void_p
 _cp = C.c_char_p
 
 GEMM_ARGTYPES = [_cp, _cp, _ip, _ip, _ip, _vp, _vp, _ip, _vp, _ip, _vp, _vp, _ip]
+RANKK_ARGTYPES = [_cp, _cp, _ip, _ip, _vp, _vp, _ip, _vp, _vp, _ip]
+RANKK_NAMES = ["ssyrk_", "dsyrk_", "csyrk_", "zsyrk_", "cherk_", "zherk_"]
 
 
 class Blat3Report(C.Structure):
@@ -33,7 +35,7 @@ class Blat3Report(C.Structure):
 
 def _build_port():
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gebp_port.c", "gebp_impl.h", "hp_ref.c", "blat3_port.c", "oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gebp_port.c", "gebp_impl.h", "hp_ref.c", "blat3_port.c", "rankk_port.c", "oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "port"], stdout=subprocess.DEVNULL)
     return so
@@ -53,6 +55,12 @@ def port():
             f = getattr(lib, "oracle_%sgemm_" % sfx)
             f.argtypes = GEMM_ARGTYPES
             f.restype = _i
+        for nm in RANKK_NAMES:
+            f = getattr(lib, "oracle_" + nm)
+            f.argtypes = RANKK_ARGTYPES
+            f.restype = _i
+        lib.oracle_xerbla_expect.argtypes = [_cp, _i]
+        lib.oracle_xerbla_result.restype = _i
         lib.oracle_gemm_omp.argtypes = [_i, C.c_char, C.c_char, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i]
         lib.oracle_hp_gemm.argtypes = [_i, C.c_char, C.c_char, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _i, _vp, _vp]
         lib.oracle_hp_gemm.restype = None
@@ -86,6 +94,10 @@ def ref_blas():
         for sfx in "sdcz":
             f = getattr(lib, "%sgemm_" % sfx)
             f.argtypes = GEMM_ARGTYPES
+            f.restype = _i
+        for nm in RANKK_NAMES:
+            f = getattr(lib, nm)
+            f.argtypes = RANKK_ARGTYPES
             f.restype = _i
         _ref_blas = lib
     return _ref_blas
@@ -159,3 +171,30 @@ def rand_matrix(rng, t, rows, cols, ld=None):
     if t in "cz":
         x = x + 1j * rng.uniform(-1, 1, size=(max(ld, 1), cols))
     return np.asfortranarray(x.astype(dt))
+
+
+def call_rankk(fn, name, uplo, trans, n, k, alpha, a, lda, beta, c, ldc):
+    """Call an F77-ABI ?syrk_/?herk_.  `name` like "dsyrk_" / "zherk_"; herk takes REAL alpha and beta."""
+    t = name[0]
+    herk = "herk" in name
+    dt = NP_DTYPE[t]
+    rdt = np.float32 if t in "sc" else np.float64
+    al = np.array([alpha], dtype=rdt if herk else dt)
+    be = np.array([beta], dtype=rdt if herk else dt)
+    ints = [C.c_int(v) for v in (n, k, lda, ldc)]
+    return fn(uplo.encode(), trans.encode(), C.byref(ints[0]), C.byref(ints[1]), _ptr(al), _ptr(a), C.byref(ints[2]),
+              _ptr(be), _ptr(c), C.byref(ints[3]))
+
+
+def hp_rankk(name, uplo, trans, n, k, alpha, a, lda, beta, c, ldc):
+    """Long-double reference of a rank-k update (full n x n result and gauge; compare on the `uplo` triangle only)."""
+    t = name[0]
+    herk = "herk" in name
+    other = ("C" if herk else "T")
+    ta, tb = ("N", other) if trans in "Nn" else (other, "N")
+    return hp_gemm(t, ta, tb, n, n, k, alpha, a, lda, a, lda, beta, c, ldc)
+
+
+def tri_mask(n, uplo):
+    i, j = np.indices((n, n))
+    return (i <= j) if uplo in "Uu" else (i >= j)

@@ -18,7 +18,7 @@ def test_header_symbols_exported():
     hdr = open(os.path.join(ROOT, "include", "b200blas.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b([a-z_0-9]+_?)\s*\(", hdr)) - {"defined"}
-    declared = {d for d in declared if d.endswith("gemm_") or d.startswith("b200blas_") or d == "xerbla_"}
+    declared = {d for d in declared if d.endswith(("gemm_", "syrk_", "herk_")) or d.startswith("b200blas_") or d == "xerbla_"}
     assert declared == set(eigen_b200.EXPORTS), declared ^ set(eigen_b200.EXPORTS)
     L = eigen_b200.lib()
     for name in declared:
@@ -58,3 +58,27 @@ def test_quick_return_m0_n0(t):
         r = oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "N", m, n, 2, 1.0, a, 4, a, 4, 0.0, c, 4)
         assert r == 0
         assert np.all(c == 7)
+
+
+@pytest.mark.parametrize("name", oa.RANKK_NAMES)
+def test_rankk_error_exits_without_gpu(name):
+    """?SYRK / ?HERK blocks of xCHKE (info 1, 2, 3, 4, 7, 10) -- argument checking precedes any CUDA work."""
+    P = oa.port()
+    L = C.CDLL(eigen_b200.LIB_PATH, mode=C.RTLD_LOCAL)
+    for nm in oa.RANKK_NAMES:
+        getattr(L, nm).argtypes = oa.RANKK_ARGTYPES
+    t = name[0]
+    herk, cplx = "herk" in name, t in "cz"
+    a = np.zeros((4, 4), dtype=oa.NP_DTYPE[t], order="F")
+    c = np.zeros((4, 4), dtype=oa.NP_DTYPE[t], order="F")
+    bad_trans = "T" if herk else ("C" if cplx else "/")
+    good_t = "C" if herk else "T"
+    cases = [(1, "/", "N", 0, 0, 1, 1), (2, "U", bad_trans, 0, 0, 1, 1), (3, "U", "N", -1, 0, 1, 1), (4, "L", good_t, 0, -1, 1, 1),
+             (7, "U", "N", 2, 0, 1, 2), (7, "L", good_t, 0, 2, 1, 1), (10, "U", "N", 2, 0, 2, 1), (10, "L", good_t, 2, 0, 1, 1)]
+    label = (name[:-1].upper() + " ").encode()
+    for (info, uplo, trans, n, k, lda, ldc) in cases:
+        P.oracle_xerbla_expect(label, info)
+        oa.call_rankk(getattr(L, name), name, uplo, trans, n, k, 1.0, a, lda, 1.0, c, ldc)
+        assert P.oracle_xerbla_result() == 1, (name, info)
+    # n == 0 returns before anything is touched
+    assert oa.call_rankk(getattr(L, name), name, "U", "N", 0, 3, 1.0, a, 4, 0.0, c, 4) == 0
