@@ -32,6 +32,31 @@ __host__ __device__ __forceinline__ bool tile_outside(int uplo, int64_t i0, int6
   return uplo == UPLO_UPPER ? (i0 > j1 - 1) : uplo == UPLO_LOWER ? (i1 - 1 < j0) : false;
 }
 
+// B := alpha * inv(op(A)) * B / alpha * op(A) * B (left) or B := alpha * B * inv(op(A)) / alpha * B * op(A) (right); A triangular
+// of order m (left) or n (right), B is m x n (?trsm_/?trmm_, blas/level3_impl.h:78-284).  Device pointers.
+struct TriProblem {
+  int type;
+  int left;          // 1: side 'L', 0: side 'R'
+  int uplo;          // UPLO_UPPER / UPLO_LOWER: the stored triangle of A
+  int op;            // OP_N / OP_T / OP_C applied to A
+  int unit;          // 1: unit diagonal, the stored diagonal is not referenced
+  int64_t m, n;
+  double alpha[2];
+  const void* A; int64_t lda;
+  void* B; int64_t ldb;
+};
+// C := alpha * A * B + beta * C (left) or alpha * B * A + beta * C (right); A symmetric (herm = 0) or Hermitian (herm = 1),
+// only its `uplo` triangle is referenced (?symm_/?hemm_, blas/level3_impl.h:287-355,505-562).  Device pointers.
+struct SymmProblem {
+  int type;
+  int left, uplo, herm;
+  int64_t m, n;
+  double alpha[2], beta[2];
+  const void* A; int64_t lda;
+  const void* B; int64_t ldb;
+  void* C; int64_t ldc;
+};
+
 static inline int type_bytes(int t) { return t == TY_S ? 4 : t == TY_Z ? 16 : 8; }
 
 // kernel launchers (one translation unit each); return cudaError_t as int, bump the launch counter themselves
@@ -42,6 +67,12 @@ size_t tf32x3_workspace_bytes(const GemmProblem& p);
 bool dmma_supported(const GemmProblem& p);
 bool tf32x3_supported(const GemmProblem& p);
 double pipe_peak(int pipe, int millis);
+// variant choice + launch of one product on device memory (host.cu); used by the composite level-3 routines
+int run_gemm_device(const GemmProblem& p, cudaStream_t s, int variant);
+int launch_trsm(const TriProblem& p, cudaStream_t s);   // tri.cu
+int launch_trmm(const TriProblem& p, cudaStream_t s);
+size_t symm_workspace_bytes(const SymmProblem& p);
+int launch_symm(const SymmProblem& p, cudaStream_t s, void* workspace);
 
 void count_launch(int n = 1);
 void note_variant(const char* name);

@@ -9,57 +9,10 @@
 // register-tiled FMA micro-kernel; the epilogue fuses alpha and beta, which the reference applies as a separate
 // pass over C (blas/level3_impl.h:62-66).
 #include "common.cuh"
+#include "scalar.cuh"
 
 namespace b200 {
 namespace {
-
-template <typename T> struct Sc;  // scalar traits
-template <> struct Sc<float> {
-  using real = float;
-  static __device__ __forceinline__ float zero() { return 0.f; }
-  static __device__ __forceinline__ float make(double re, double) { return (float)re; }
-  static __device__ __forceinline__ float conj(float a) { return a; }
-  static __device__ __forceinline__ void fma(float& c, float a, float b) { c = fmaf(a, b, c); }
-  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
-  static __device__ __forceinline__ bool is_zero(float a) { return a == 0.f; }
-};
-template <> struct Sc<double> {
-  using real = double;
-  static __device__ __forceinline__ double zero() { return 0.0; }
-  static __device__ __forceinline__ double make(double re, double) { return re; }
-  static __device__ __forceinline__ double conj(double a) { return a; }
-  static __device__ __forceinline__ void fma(double& c, double a, double b) { c = ::fma(a, b, c); }
-  static __device__ __forceinline__ double mul(double a, double b) { return a * b; }
-  static __device__ __forceinline__ bool is_zero(double a) { return a == 0.0; }
-};
-template <> struct Sc<float2> {
-  using real = float;
-  static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
-  static __device__ __forceinline__ float2 make(double re, double im) { return make_float2((float)re, (float)im); }
-  static __device__ __forceinline__ float2 conj(float2 a) { return make_float2(a.x, -a.y); }
-  static __device__ __forceinline__ void fma(float2& c, float2 a, float2 b) {
-    c.x = fmaf(a.x, b.x, c.x); c.x = fmaf(-a.y, b.y, c.x);
-    c.y = fmaf(a.x, b.y, c.y); c.y = fmaf(a.y, b.x, c.y);
-  }
-  static __device__ __forceinline__ float2 mul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-  }
-  static __device__ __forceinline__ bool is_zero(float2 a) { return a.x == 0.f && a.y == 0.f; }
-};
-template <> struct Sc<double2> {
-  using real = double;
-  static __device__ __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
-  static __device__ __forceinline__ double2 make(double re, double im) { return make_double2(re, im); }
-  static __device__ __forceinline__ double2 conj(double2 a) { return make_double2(a.x, -a.y); }
-  static __device__ __forceinline__ void fma(double2& c, double2 a, double2 b) {
-    c.x = ::fma(a.x, b.x, c.x); c.x = ::fma(-a.y, b.y, c.x);
-    c.y = ::fma(a.x, b.y, c.y); c.y = ::fma(a.y, b.x, c.y);
-  }
-  static __device__ __forceinline__ double2 mul(double2 a, double2 b) {
-    return make_double2(::fma(a.x, b.x, -a.y * b.y), ::fma(a.x, b.y, a.y * b.x));
-  }
-  static __device__ __forceinline__ bool is_zero(double2 a) { return a.x == 0.0 && a.y == 0.0; }
-};
 
 // Thread block = 16 x 16 threads.  Each thread owns RM x RN chunks of VE x VE results, VE = 16 bytes / sizeof(T):
 // chunk (cm, cn) covers rows cm*16*VE + tx*VE + [0,VE) and columns cn*16*VE + ty*VE + [0,VE).  With this layout

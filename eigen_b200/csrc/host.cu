@@ -92,6 +92,9 @@ static void keep_pool_memory() {
   done_dev = dev;
 }
 
+static int run_device(const GemmProblem& p, cudaStream_t s, int variant);
+int run_gemm_device(const GemmProblem& p, cudaStream_t s, int variant) { return run_device(p, s, variant); }
+
 static int run_device(const GemmProblem& p, cudaStream_t s, int variant) {
   const int v = choose_variant(p, variant);
   if (v == B200BLAS_DMMA) return fail(launch_dmma(p, s));
@@ -689,6 +692,260 @@ static int rankk_entry(int type, bool herk, const char* uplo, const char* op, co
   return 0;
 }
 
+
+// ---- the remaining level-3 routines: whole-operand staging ------------------------------------------
+// ?trsm_ ?trmm_ ?symm_ ?hemm_ ?syr2k_ ?her2k_ are composites of the GEMM kernels (tri.cu, masked products); their host
+// path uploads the operands whole, computes on s_comp and brings the result window back (no slab pipeline yet).
+static int side_of(char x) { return (x == 'L' || x == 'l') ? 1 : (x == 'R' || x == 'r') ? 0 : -1; }
+static int uplo_of(char x) { return (x == 'U' || x == 'u') ? UPLO_UPPER : (x == 'L' || x == 'l') ? UPLO_LOWER : -1; }
+static int diag_of(char x) { return (x == 'U' || x == 'u') ? 1 : (x == 'N' || x == 'n') ? 0 : -1; }
+
+// upload a rows x cols host window into staging slot `slot`; *dld receives the device leading dimension
+static int stage_in(Staging& st, int slot, const void* h, int64_t ld, int64_t rows, int64_t cols, size_t es, bool copy, int64_t* dld) {
+  const int64_t q = 32 / (int64_t)es > 0 ? 32 / (int64_t)es : 1;
+  *dld = round_up(std::max<int64_t>(rows, 1), q);
+  { const int e = st.reserve(slot, (size_t)*dld * (size_t)std::max<int64_t>(cols, 1) * es); if (e) return e; }
+  if (!copy || rows == 0 || cols == 0) return 0;
+  char* d = (char*)st.dbuf[slot];
+  const bool paged = (size_t)rows * cols * es >= ((size_t)4 << 20) && is_pageable(h);
+  if (paged) { const int e = st.ring_in.h2d(d, (size_t)*dld * es, (const char*)h, (size_t)ld * es, (size_t)rows * es, (size_t)cols, st.s_in); if (e) return e; }
+  else B200_CUDA_TRY(cudaMemcpy2DAsync(d, (size_t)*dld * es, h, (size_t)ld * es, (size_t)rows * es, (size_t)cols, cudaMemcpyHostToDevice, st.s_in));
+  t_h2d += (uint64_t)rows * cols * es;
+  return 0;
+}
+static int stage_out(Staging& st, int slot, void* h, int64_t ld, int64_t rows, int64_t cols, size_t es, int64_t dld) {
+  const char* d = (const char*)st.dbuf[slot];
+  const bool paged = (size_t)rows * cols * es >= ((size_t)4 << 20) && is_pageable(h);
+  if (paged) { const int e = st.ring_out.d2h((char*)h, (size_t)ld * es, d, (size_t)dld * es, (size_t)rows * es, (size_t)cols, st.s_out); if (e) return e; }
+  else {
+    B200_CUDA_TRY(cudaMemcpy2DAsync(h, (size_t)ld * es, d, (size_t)dld * es, (size_t)rows * es, (size_t)cols, cudaMemcpyDeviceToHost, st.s_out));
+    B200_CUDA_TRY(cudaStreamSynchronize(st.s_out));
+  }
+  t_d2h += (uint64_t)rows * cols * es;
+  return 0;
+}
+static int inputs_ready(Staging& st) {
+  B200_CUDA_TRY(cudaEventRecord(st.ev_in[0], st.s_in));
+  return (int)cudaStreamWaitEvent(st.s_comp, st.ev_in[0], 0);
+}
+
+static int symm_on_stream(const SymmProblem& p, cudaStream_t s) {
+  const size_t ws = symm_workspace_bytes(p);
+  void* w = nullptr;
+  keep_pool_memory();
+  { const int e = (int)cudaMallocAsync(&w, ws ? ws : 16, s); if (e) return e; }
+  const int e = launch_symm(p, s, w);
+  cudaFreeAsync(w, s);
+  return e;
+}
+
+static const char* k_trsm_names[4] = {"STRSM ", "DTRSM ", "CTRSM ", "ZTRSM "};
+static const char* k_trmm_names[4] = {"STRMM ", "DTRMM ", "CTRMM ", "ZTRMM "};
+
+// blas/level3_impl.h:78-178 (trsm) and :183-284 (trmm)
+static int tri_entry(int type, bool solve, const char* side, const char* uplo, const char* opa, const char* diag, const int* pm,
+                     const int* pn, const void* palpha, const void* a, const int* plda, void* b, const int* pldb) {
+  const char* name = solve ? k_trsm_names[type] : k_trmm_names[type];
+  const int sd = side_of(*side), ul = uplo_of(*uplo), o = op_of(*opa), dg = diag_of(*diag);
+  int info = 0;
+  if (sd < 0) info = 1;
+  else if (ul < 0) info = 2;
+  else if (o == OP_INVALID) info = 3;
+  else if (dg < 0) info = 4;
+  else if (*pm < 0) info = 5;
+  else if (*pn < 0) info = 6;
+  else if (*plda < std::max(1, sd ? *pm : *pn)) info = 9;
+  else if (*pldb < std::max(1, *pm)) info = 11;
+  if (info) return xerbla_(name, &info, 6);
+  const int ret = solve ? 0 : 1;   // the reference's ?trmm_ returns 1 (level3_impl.h:265,283); Fortran callers ignore it
+  if (*pm == 0 || *pn == 0) return ret;
+  TriProblem p;
+  p.type = type; p.left = sd; p.uplo = ul; p.op = o; p.unit = dg; p.m = *pm; p.n = *pn;
+  load_scalar(type, palpha, p.alpha);
+  p.A = a; p.lda = *plda; p.B = b; p.ldb = *pldb;
+  const bool alpha_zero = p.alpha[0] == 0.0 && p.alpha[1] == 0.0;
+  t_error[0] = 0;
+  int err = 0;
+  const bool dev_b = is_device_ptr(b);
+  if (!alpha_zero && is_device_ptr(a) != dev_b) {
+    snprintf(t_error, sizeof t_error, "operands must be all host or all device pointers");
+    info = -1;
+    return xerbla_(name, &info, 6);
+  }
+  if (dev_b) {
+    err = fail(solve ? launch_trsm(p, nullptr) : launch_trmm(p, nullptr));
+    if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
+  } else {
+    std::lock_guard<std::mutex> lock(g_stage.mu);
+    Staging& st = g_stage;
+    err = st.init();
+    const size_t es = (size_t)type_bytes(type);
+    const int64_t na = sd ? p.m : p.n;
+    int64_t dlda = 0, dldb = 0;
+    t_h2d = t_d2h = 0;
+    if (!err) err = stage_in(st, 0, a, *plda, na, na, es, !alpha_zero, &dlda);
+    if (!err) err = stage_in(st, 2, b, *pldb, p.m, p.n, es, !alpha_zero, &dldb);
+    if (!err) err = inputs_ready(st);
+    if (!err) {
+      TriProblem d = p;
+      d.A = st.dbuf[0]; d.lda = dlda; d.B = st.dbuf[2]; d.ldb = dldb;
+      err = solve ? launch_trsm(d, st.s_comp) : launch_trmm(d, st.s_comp);
+    }
+    if (!err) err = (int)cudaStreamSynchronize(st.s_comp);
+    if (!err) err = stage_out(st, 2, b, *pldb, p.m, p.n, es, dldb);
+    if (err) cudaDeviceSynchronize();
+    err = fail(err);
+  }
+  if (err) { info = -1; return xerbla_(name, &info, 6); }
+  return ret;
+}
+
+static const char* k_symm_names[4] = {"SSYMM ", "DSYMM ", "CSYMM ", "ZSYMM "};
+static const char* k_hemm_names[4] = {"", "", "CHEMM ", "ZHEMM "};
+
+// blas/level3_impl.h:287-355 (symm) and :505-562 (hemm)
+static int symm_entry(int type, bool herm, const char* side, const char* uplo, const int* pm, const int* pn, const void* palpha,
+                      const void* a, const int* plda, const void* b, const int* pldb, const void* pbeta, void* c, const int* pldc) {
+  const char* name = herm ? k_hemm_names[type] : k_symm_names[type];
+  const int sd = side_of(*side), ul = uplo_of(*uplo);
+  int info = 0;
+  if (sd < 0) info = 1;
+  else if (ul < 0) info = 2;
+  else if (*pm < 0) info = 3;
+  else if (*pn < 0) info = 4;
+  else if (*plda < std::max(1, sd ? *pm : *pn)) info = 7;
+  else if (*pldb < std::max(1, *pm)) info = 9;
+  else if (*pldc < std::max(1, *pm)) info = 12;
+  if (info) return xerbla_(name, &info, 6);
+  if (*pm == 0 || *pn == 0) return 1;   // level3_impl.h:316-319, :531-534
+  SymmProblem p;
+  p.type = type; p.left = sd; p.uplo = ul; p.herm = herm ? 1 : 0; p.m = *pm; p.n = *pn;
+  load_scalar(type, palpha, p.alpha);
+  load_scalar(type, pbeta, p.beta);
+  p.A = a; p.lda = *plda; p.B = b; p.ldb = *pldb; p.C = c; p.ldc = *pldc;
+  const bool alpha_zero = p.alpha[0] == 0.0 && p.alpha[1] == 0.0;
+  const bool beta_zero = p.beta[0] == 0.0 && p.beta[1] == 0.0;
+  t_error[0] = 0;
+  int err = 0;
+  const bool dev_c = is_device_ptr(c);
+  if (!alpha_zero && (is_device_ptr(a) != dev_c || is_device_ptr(b) != dev_c)) {
+    snprintf(t_error, sizeof t_error, "operands must be all host or all device pointers");
+    info = -1;
+    return xerbla_(name, &info, 6);
+  }
+  // alpha == 0: only the beta pass remains (netlib quick path) -- a k = 0 product on the GEMM kernels
+  auto beta_only = [&](void* dC, int64_t dldc, cudaStream_t s) {
+    GemmProblem g;
+    g.type = type; g.opa = OP_N; g.opb = OP_N; g.m = p.m; g.n = p.n; g.k = 0;
+    g.alpha[0] = g.alpha[1] = 0.0; g.beta[0] = p.beta[0]; g.beta[1] = p.beta[1];
+    g.A = nullptr; g.lda = 1; g.B = nullptr; g.ldb = 1; g.C = dC; g.ldc = dldc;
+    return run_device(g, s, B200BLAS_AUTO);
+  };
+  if (dev_c) {
+    err = alpha_zero ? beta_only(c, *pldc, nullptr) : fail(symm_on_stream(p, nullptr));
+    if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
+  } else {
+    std::lock_guard<std::mutex> lock(g_stage.mu);
+    Staging& st = g_stage;
+    err = st.init();
+    const size_t es = (size_t)type_bytes(type);
+    const int64_t na = sd ? p.m : p.n;
+    int64_t dlda = 0, dldb = 0, dldc = 0;
+    t_h2d = t_d2h = 0;
+    if (!err) err = stage_in(st, 0, a, *plda, na, na, es, !alpha_zero, &dlda);
+    if (!err) err = stage_in(st, 1, b, *pldb, p.m, p.n, es, !alpha_zero, &dldb);
+    if (!err) err = stage_in(st, 2, c, *pldc, p.m, p.n, es, !beta_zero, &dldc);
+    if (!err) err = inputs_ready(st);
+    if (!err) {
+      SymmProblem d = p;
+      d.A = st.dbuf[0]; d.lda = dlda; d.B = st.dbuf[1]; d.ldb = dldb; d.C = st.dbuf[2]; d.ldc = dldc;
+      err = alpha_zero ? beta_only(st.dbuf[2], dldc, st.s_comp) : symm_on_stream(d, st.s_comp);
+    }
+    if (!err) err = (int)cudaStreamSynchronize(st.s_comp);
+    if (!err) err = stage_out(st, 2, c, *pldc, p.m, p.n, es, dldc);
+    if (err) cudaDeviceSynchronize();
+    err = fail(err);
+  }
+  if (err) { info = -1; return xerbla_(name, &info, 6); }
+  return 0;
+}
+
+static const char* k_syr2k_names[4] = {"SSYR2K", "DSYR2K", "CSYR2K", "ZSYR2K"};
+static const char* k_her2k_names[4] = {"", "", "CHER2K", "ZHER2K"};
+
+// blas/level3_impl.h:437-503 (syr2k) and :631-700 (her2k): two masked products on the GEMM kernels,
+//   C.tri = alpha * op(A) op(B)^T|^H + beta * C.tri,   then   C.tri += alpha|conj(alpha) * op(B) op(A)^T|^H
+static int r2k_entry(int type, bool her, const char* uplo, const char* op, const int* pn, const int* pk, const void* palpha,
+                     const void* a, const int* plda, const void* b, const int* pldb, const void* pbeta, void* c, const int* pldc) {
+  const bool cplx = (type == TY_C || type == TY_Z);
+  const char* name = her ? k_her2k_names[type] : k_syr2k_names[type];
+  const int ul = uplo_of(*uplo), o = op_of(*op);
+  int info = 0;
+  if (ul < 0) info = 1;
+  else if (o == OP_INVALID || (!her && cplx && o == OP_C) || (her && o == OP_T)) info = 2;
+  else if (*pn < 0) info = 3;
+  else if (*pk < 0) info = 4;
+  else if (*plda < std::max(1, o == OP_N ? *pn : *pk)) info = 7;
+  else if (*pldb < std::max(1, o == OP_N ? *pn : *pk)) info = 9;
+  else if (*pldc < std::max(1, *pn)) info = 12;
+  if (info) return xerbla_(name, &info, 6);
+  if (*pn == 0) return 0;
+  double alpha[2], beta[2];
+  load_scalar(type, palpha, alpha);
+  if (her) { beta[0] = (type == TY_C) ? (double)*(const float*)pbeta : *(const double*)pbeta; beta[1] = 0.0; }   // REAL beta
+  else load_scalar(type, pbeta, beta);
+  const bool alpha_zero = alpha[0] == 0.0 && alpha[1] == 0.0;
+  const bool beta_one = beta[0] == 1.0 && beta[1] == 0.0, beta_zero = beta[0] == 0.0 && beta[1] == 0.0;
+  const bool product = *pk > 0 && !alpha_zero;
+  if (!product && beta_one) return her || *pk == 0 ? 1 : 0;   // C untouched (including a Hermitian diagonal)
+  const int64_t n = *pn, k = product ? *pk : 0;
+  const int tr = her ? OP_C : OP_T;
+  t_error[0] = 0;
+  const bool dev_c = is_device_ptr(c);
+  if (product && (is_device_ptr(a) != dev_c || is_device_ptr(b) != dev_c)) {
+    snprintf(t_error, sizeof t_error, "operands must be all host or all device pointers");
+    info = -1;
+    return xerbla_(name, &info, 6);
+  }
+  auto run = [&](const void* dA, int64_t dlda, const void* dB, int64_t dldb, void* dC, int64_t dldc, cudaStream_t s) -> int {
+    GemmProblem g;
+    g.type = type; g.m = n; g.n = n; g.k = k; g.uplo = ul; g.herm = her ? 1 : 0;
+    if (o == OP_N) { g.opa = OP_N; g.opb = tr; } else { g.opa = tr; g.opb = OP_N; }
+    g.alpha[0] = alpha[0]; g.alpha[1] = alpha[1]; g.beta[0] = beta[0]; g.beta[1] = beta[1];
+    g.A = dA; g.lda = dlda; g.B = dB; g.ldb = dldb; g.C = dC; g.ldc = dldc;
+    { const int e = run_device(g, s, B200BLAS_AUTO); if (e) return e; }
+    if (k == 0) return 0;
+    g.A = dB; g.lda = dldb; g.B = dA; g.ldb = dlda;
+    if (her) g.alpha[1] = -alpha[1];
+    g.beta[0] = 1.0; g.beta[1] = 0.0;
+    return run_device(g, s, B200BLAS_AUTO);
+  };
+  int err = 0;
+  if (dev_c) {
+    err = run(a, *plda, b, *pldb, c, *pldc, nullptr);
+    if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
+  } else {
+    std::lock_guard<std::mutex> lock(g_stage.mu);
+    Staging& st = g_stage;
+    err = st.init();
+    const size_t es = (size_t)type_bytes(type);
+    const int64_t ra = (o == OP_N) ? n : *pk, ca = (o == OP_N) ? *pk : n;
+    int64_t dlda = 0, dldb = 0, dldc = 0;
+    t_h2d = t_d2h = 0;
+    if (!err) err = stage_in(st, 0, a, *plda, ra, ca, es, product, &dlda);
+    if (!err) err = stage_in(st, 1, b, *pldb, ra, ca, es, product, &dldb);
+    if (!err) err = stage_in(st, 2, c, *pldc, n, n, es, !beta_zero, &dldc);
+    if (!err) err = inputs_ready(st);
+    if (!err) err = run(st.dbuf[0], dlda, st.dbuf[1], dldb, st.dbuf[2], dldc, st.s_comp);
+    if (!err) err = (int)cudaStreamSynchronize(st.s_comp);
+    if (!err) { err = ring_d2h_triangle(st.ring_out, (char*)c, (size_t)*pldc * es, (const char*)st.dbuf[2], (size_t)dldc * es, (size_t)n, es, ul, st.s_out); t_d2h += (uint64_t)n * (n + 1) / 2 * es; }
+    if (err) cudaDeviceSynchronize();
+    err = fail(err);
+  }
+  if (err) { info = -1; return xerbla_(name, &info, 6); }
+  return (her || *pk == 0) ? 1 : 0;   // return values of level3_impl.h:470-471,502 / :672-673,699
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -718,6 +975,31 @@ int zgemm_(const char* ta, const char* tb, const int* m, const int* n, const int
            const int* ldc) {
   return gemm_entry(TY_Z, ta, tb, m, n, k, alpha, a, lda, b, ldb, beta, c, ldc);
 }
+
+#define B200_TRI(NAME, TYPE, SOLVE, RT)                                                                                            \
+  int NAME(const char* side, const char* uplo, const char* opa, const char* diag, const int* m, const int* n, const RT* alpha,  \
+           const RT* a, const int* lda, RT* b, const int* ldb) {                                                                \
+    return tri_entry(TYPE, SOLVE, side, uplo, opa, diag, m, n, alpha, a, lda, b, ldb);                                          \
+  }
+B200_TRI(strsm_, TY_S, true, float) B200_TRI(dtrsm_, TY_D, true, double) B200_TRI(ctrsm_, TY_C, true, float) B200_TRI(ztrsm_, TY_Z, true, double)
+B200_TRI(strmm_, TY_S, false, float) B200_TRI(dtrmm_, TY_D, false, double) B200_TRI(ctrmm_, TY_C, false, float) B200_TRI(ztrmm_, TY_Z, false, double)
+#undef B200_TRI
+#define B200_SYMM(NAME, TYPE, HERM, RT)                                                                                          \
+  int NAME(const char* side, const char* uplo, const int* m, const int* n, const RT* alpha, const RT* a, const int* lda,         \
+           const RT* b, const int* ldb, const RT* beta, RT* c, const int* ldc) {                                                 \
+    return symm_entry(TYPE, HERM, side, uplo, m, n, alpha, a, lda, b, ldb, beta, c, ldc);                                        \
+  }
+B200_SYMM(ssymm_, TY_S, false, float) B200_SYMM(dsymm_, TY_D, false, double) B200_SYMM(csymm_, TY_C, false, float) B200_SYMM(zsymm_, TY_Z, false, double)
+B200_SYMM(chemm_, TY_C, true, float) B200_SYMM(zhemm_, TY_Z, true, double)
+#undef B200_SYMM
+#define B200_R2K(NAME, TYPE, HER, RT)                                                                                            \
+  int NAME(const char* uplo, const char* trans, const int* n, const int* k, const RT* alpha, const RT* a, const int* lda,        \
+           const RT* b, const int* ldb, const RT* beta, RT* c, const int* ldc) {                                                 \
+    return r2k_entry(TYPE, HER, uplo, trans, n, k, alpha, a, lda, b, ldb, beta, c, ldc);                                         \
+  }
+B200_R2K(ssyr2k_, TY_S, false, float) B200_R2K(dsyr2k_, TY_D, false, double) B200_R2K(csyr2k_, TY_C, false, float) B200_R2K(zsyr2k_, TY_Z, false, double)
+B200_R2K(cher2k_, TY_C, true, float) B200_R2K(zher2k_, TY_Z, true, double)
+#undef B200_R2K
 
 int ssyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
            const float* beta, float* c, const int* ldc) { return rankk_entry(TY_S, false, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }

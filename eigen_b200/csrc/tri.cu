@@ -1,0 +1,301 @@
+// eigen_b200/csrc/tri.cu -- triangular solve / multiply and symmetric products built on the GEMM kernels (sm_100a).
+//
+// SURVEY.md section 8 rows f2 (trsm) and f4 (trmm, symm/hemm).  Reference being replaced:
+//   triangular_solve_matrix            Eigen/src/Core/products/TriangularSolverMatrix.h:41-335   (?trsm_, blas/level3_impl.h:78-178)
+//   product_triangular_matrix_matrix   Eigen/src/Core/products/TriangularMatrixMatrix.h:89-383   (?trmm_, blas/level3_impl.h:183-284)
+//   product_selfadjoint_matrix         Eigen/src/Core/products/SelfadjointMatrixMatrix.h:19-455  (?symm_/?hemm_, level3_impl.h:287-355,505-562)
+// The reference blocks the triangle into small panels solved by substitution and pushes everything else through
+// gebp_kernel.  Here the same split is recursive: a triangle of order d is cut at d1 (a power-of-two multiple of the
+// leaf order), the off-diagonal block becomes ONE large product on the tensor-pipe GEMM kernels (gemm_dmma.cu /
+// gemm_tf32x3.cu) and only leaves of order <= NB are handled by a register-resident substitution kernel, one
+// right-hand-side vector per thread.  Symmetric / Hermitian operands are expanded from the referenced triangle into a
+// dense device image (what blas/level3_impl.h:324-341 does on the host for the complex case) and multiplied by the
+// GEMM kernels.
+#include "../../include/b200blas.h"
+#include "common.cuh"
+#include "scalar.cuh"
+
+namespace b200 {
+namespace {
+
+// ---- leaf: S x = b (SOLVE) or x := S b (multiply) for every right-hand-side vector ---------------------------------------------
+// S is the NB x NB canonical matrix that multiplies a right-hand-side VECTOR from the left:
+//   side = left :  S = op(A) block,      vectors = columns of B
+//   side = right:  S = op(A)^T block,    vectors = rows of B          (X op(A) = B  <=>  op(A)^T X^T = B^T)
+// Entries outside the referenced triangle are zero, a unit diagonal is one, and rows/columns past nb are the identity,
+// so the fully unrolled NB-step recurrence is valid for every nb <= NB.  In SOLVE mode the diagonal holds reciprocals
+// (the reference multiplies by 1/diag as well, TriangularSolverMatrix.h:118-121).
+template <typename T, int NB, bool LOWER, bool SOLVE>
+__global__ void __launch_bounds__(64)
+tri_leaf_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrhs, const T* __restrict__ A, int64_t lda,
+                T* __restrict__ B, int64_t ldb) {
+  __shared__ T S[NB][NB];
+  for (int idx = threadIdx.x; idx < NB * NB; idx += 64) {
+    const int i = idx % NB, j = idx / NB;
+    T v = (i == j) ? sc_one<T>() : Sc<T>::zero();
+    if (i < nb && j < nb) {
+      const bool swap = left ? (op != OP_N) : (op == OP_N);
+      const int r = swap ? j : i, c = swap ? i : j;   // element of A
+      const bool referenced = (r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c);
+      if (referenced) {
+        v = A[r + c * lda];
+        if (op == OP_C) v = Sc<T>::conj(v);
+        if (SOLVE && r == c) v = sc_recip<T>(v);
+      } else if (r != c) {
+        v = Sc<T>::zero();
+      }
+    }
+    S[i][j] = v;
+  }
+  __syncthreads();
+  const int64_t v = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  if (v >= nrhs) return;
+  T* bp = left ? B + v * ldb : B + v;
+  const int64_t bs = left ? 1 : ldb;
+  T x[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) x[i] = (i < nb) ? bp[i * bs] : Sc<T>::zero();
+  if constexpr (SOLVE) {
+    if constexpr (LOWER) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        x[j] = Sc<T>::mul(x[j], S[j][j]);
+#pragma unroll
+        for (int i = j + 1; i < NB; ++i) sc_fnma<T>(x[i], S[i][j], x[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = NB - 1; j >= 0; --j) {
+        x[j] = Sc<T>::mul(x[j], S[j][j]);
+#pragma unroll
+        for (int i = 0; i < j; ++i) sc_fnma<T>(x[i], S[i][j], x[j]);
+      }
+    }
+  } else {
+    if constexpr (LOWER) {   // x_i := sum_{j <= i} S_ij x_j, bottom-up so the inputs are still intact
+#pragma unroll
+      for (int i = NB - 1; i >= 0; --i) {
+        T acc = Sc<T>::mul(S[i][i], x[i]);
+#pragma unroll
+        for (int j = 0; j < i; ++j) Sc<T>::fma(acc, S[i][j], x[j]);
+        x[i] = acc;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        T acc = Sc<T>::mul(S[i][i], x[i]);
+#pragma unroll
+        for (int j = i + 1; j < NB; ++j) Sc<T>::fma(acc, S[i][j], x[j]);
+        x[i] = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NB; ++i)
+    if (i < nb) bp[i * bs] = x[i];
+}
+
+// ---- B := alpha * B (alpha == 0: B := 0 without reading it) over an m x n window -----------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) window_scale_kernel(int64_t m, int64_t n, T alpha, bool zero, T* __restrict__ B, int64_t ldb) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= m) return;
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+    T* p = B + i + j * ldb;
+    *p = zero ? Sc<T>::zero() : Sc<T>::mul(alpha, *p);
+  }
+}
+
+// ---- dense image of a symmetric / Hermitian matrix given by one triangle -------------------------------------------------------
+// 32 x 32 tiles; a tile in the unreferenced triangle is the (conjugate) transpose of its mirror tile, read coalesced
+// and transposed through shared memory.  Hermitian: the imaginary part of the diagonal is taken as zero (BLAS contract).
+template <typename T>
+__global__ void __launch_bounds__(256) symm_expand_kernel(int uplo, int herm, int64_t n, const T* __restrict__ A, int64_t lda,
+                                                          T* __restrict__ W, int64_t ldw) {
+  __shared__ T tile[32][33];
+  const int64_t ti = blockIdx.x, tj = blockIdx.y;   // tile of W: rows ti*32.., columns tj*32..
+  const bool mirrored = (uplo == UPLO_UPPER) ? (ti > tj) : (ti < tj);
+  const int64_t si = mirrored ? tj : ti, sj = mirrored ? ti : tj;   // source tile of A
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+  for (int c = ty; c < 32; c += 8) {
+    const int64_t gi = si * 32 + tx, gj = sj * 32 + c;
+    const bool referenced = gi < n && gj < n && (gi == gj || (uplo == UPLO_UPPER ? gi < gj : gi > gj));
+    tile[c][tx] = referenced ? A[gi + gj * lda] : Sc<T>::zero();   // tile[col][row] of the source tile
+  }
+  __syncthreads();
+  for (int c = ty; c < 32; c += 8) {
+    const int64_t gi = ti * 32 + tx, gj = tj * 32 + c;
+    if (gi >= n || gj >= n) continue;
+    T v;
+    if (ti != tj) {
+      v = mirrored ? tile[tx][c] : tile[c][tx];
+      if (mirrored && herm) v = Sc<T>::conj(v);
+    } else {
+      const bool referenced = (gi == gj) || (uplo == UPLO_UPPER ? gi < gj : gi > gj);
+      v = referenced ? tile[c][tx] : tile[tx][c];
+      if (!referenced && herm) v = Sc<T>::conj(v);
+      if constexpr (sizeof(T) != sizeof(typename Sc<T>::real)) { if (herm && gi == gj) v.y = 0; }
+    }
+    W[gi + gj * ldw] = v;
+  }
+}
+
+template <typename T> struct LeafOrder { static constexpr int NB = 32; };
+template <> struct LeafOrder<double2> { static constexpr int NB = 16; };
+
+template <typename T>
+T scalar_of(const double a[2]) {
+  if constexpr (sizeof(T) == sizeof(typename Sc<T>::real)) return (T)a[0];
+  else { T r; r.x = (typename Sc<T>::real)a[0]; r.y = (typename Sc<T>::real)a[1]; return r; }
+}
+
+template <typename T, bool SOLVE>
+int launch_leaf(const TriProblem& p, bool s_lower, int64_t d0, int nb, cudaStream_t s) {
+  constexpr int NB = LeafOrder<T>::NB;
+  const T* A = (const T*)p.A + d0 + d0 * p.lda;
+  T* B = p.left ? (T*)p.B + d0 : (T*)p.B + d0 * p.ldb;
+  const int64_t nrhs = p.left ? p.n : p.m;
+  const unsigned grid = (unsigned)((nrhs + 63) / 64);
+  if (s_lower)
+    tri_leaf_kernel<T, NB, true, SOLVE><<<grid, 64, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+  else
+    tri_leaf_kernel<T, NB, false, SOLVE><<<grid, 64, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+// block (r0.., c0..) of T = op(A) as a GEMM operand
+template <typename T>
+const void* tblock(const TriProblem& p, int64_t r0, int64_t c0) {
+  return (p.op == OP_N) ? (const void*)((const T*)p.A + r0 + c0 * p.lda) : (const void*)((const T*)p.A + c0 + r0 * p.lda);
+}
+
+// dst(rows rd.., or columns) += sign * T(block) * src   /   src * T(block)
+template <typename T>
+int offdiag_update(const TriProblem& p, int64_t dst0, int64_t ndst, int64_t src0, int64_t nsrc, double sign, cudaStream_t s) {
+  GemmProblem g;
+  g.type = p.type;
+  g.alpha[0] = sign; g.alpha[1] = 0.0; g.beta[0] = 1.0; g.beta[1] = 0.0;
+  if (p.left) {   // B[dst rows, :] += sign * T[dst, src] * B[src rows, :]
+    g.opa = p.op; g.opb = OP_N; g.m = ndst; g.n = p.n; g.k = nsrc;
+    g.A = tblock<T>(p, dst0, src0); g.lda = p.lda;
+    g.B = (const T*)p.B + src0; g.ldb = p.ldb;
+    g.C = (T*)p.B + dst0; g.ldc = p.ldb;
+  } else {        // B[:, dst cols] += sign * B[:, src cols] * T[src, dst]
+    g.opa = OP_N; g.opb = p.op; g.m = p.m; g.n = ndst; g.k = nsrc;
+    g.A = (const T*)p.B + src0 * p.ldb; g.lda = p.ldb;
+    g.B = tblock<T>(p, src0, dst0); g.ldb = p.lda;
+    g.C = (T*)p.B + dst0 * p.ldb; g.ldc = p.ldb;
+  }
+  return run_gemm_device(g, s, B200BLAS_AUTO);
+}
+
+static int64_t split_point(int64_t d, int nb) {   // largest nb * 2^j strictly below d
+  int64_t h = nb;
+  while (h * 2 < d) h *= 2;
+  return h;
+}
+
+// Triangle rows/columns [d0, d0 + d).  t_lower: op(A) is lower triangular.
+template <typename T, bool SOLVE>
+int tri_recurse(const TriProblem& p, bool t_lower, int64_t d0, int64_t d, cudaStream_t s) {
+  constexpr int NB = LeafOrder<T>::NB;
+  const bool s_lower = p.left ? t_lower : !t_lower;   // S = T (left) or T^T (right)
+  if (d <= NB) return launch_leaf<T, SOLVE>(p, s_lower, d0, (int)d, s);
+  const int64_t d1 = split_point(d, NB), d2 = d - d1;
+  // which diagonal block goes first: in a solve, the one whose unknowns feed the other; in a product (in place), the
+  // one whose inputs are not needed by the other any more
+  // solve, left:  T lower -> (1) first; T upper -> (2) first.   solve, right: X T = B: T lower -> (2) first; upper -> (1).
+  // multiply, left:  B2' = T21 B1 + T22 B2 (lower) -> (2) first; upper -> (1) first.   right: lower -> (1) first; upper -> (2).
+  const bool first_is_1 = SOLVE ? (p.left ? t_lower : !t_lower) : (p.left ? !t_lower : t_lower);
+  const int64_t f0 = first_is_1 ? d0 : d0 + d1, fd = first_is_1 ? d1 : d2;
+  const int64_t g0 = first_is_1 ? d0 + d1 : d0, gd = first_is_1 ? d2 : d1;
+  if constexpr (SOLVE) {
+    B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, f0, fd, s)));
+    B200_CUDA_TRY(offdiag_update<T>(p, g0, gd, f0, fd, -1.0, s));      // remaining block -= T[.,.] * solved block
+    B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, g0, gd, s)));
+  } else {
+    B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, f0, fd, s)));      // diagonal part of the first block
+    B200_CUDA_TRY(offdiag_update<T>(p, f0, fd, g0, gd, 1.0, s));       // first block += T[.,.] * (still original) other block
+    B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, g0, gd, s)));
+  }
+  return 0;
+}
+
+template <typename T>
+int scale_window(int64_t m, int64_t n, const double alpha[2], T* B, int64_t ldb, cudaStream_t s) {
+  if (alpha[0] == 1.0 && alpha[1] == 0.0) return 0;
+  const bool zero = alpha[0] == 0.0 && alpha[1] == 0.0;
+  dim3 grid((unsigned)((m + 255) / 256), (unsigned)std::min<int64_t>(n, 1024));
+  window_scale_kernel<T><<<grid, 256, 0, s>>>(m, n, scalar_of<T>(alpha), zero, B, ldb);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+template <typename T, bool SOLVE>
+int run_tri(const TriProblem& p, cudaStream_t s) {
+  const bool zero = p.alpha[0] == 0.0 && p.alpha[1] == 0.0;
+  if (!zero) {   // alpha == 0: the result is zero whatever A holds (netlib ?TRSM/?TRMM quick path)
+    const bool t_lower = (p.uplo == UPLO_LOWER) == (p.op == OP_N);
+    B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, 0, p.left ? p.m : p.n, s)));
+  }
+  // the reference scales after the solve / inside the product (blas/level3_impl.h:174-175, :278-281)
+  return scale_window<T>(p.m, p.n, p.alpha, (T*)p.B, p.ldb, s);
+}
+
+template <bool SOLVE>
+int dispatch_tri(const TriProblem& p, cudaStream_t s) {
+  if (p.m <= 0 || p.n <= 0) return 0;
+  note_variant(SOLVE ? "trsm_recursive_leaf+gemm" : "trmm_recursive_leaf+gemm");
+  switch (p.type) {
+    case TY_S: return run_tri<float, SOLVE>(p, s);
+    case TY_D: return run_tri<double, SOLVE>(p, s);
+    case TY_C: return run_tri<float2, SOLVE>(p, s);
+    default: return run_tri<double2, SOLVE>(p, s);
+  }
+}
+
+template <typename T>
+int expand_typed(const SymmProblem& p, int64_t na, void* W, int64_t ldw, cudaStream_t s) {
+  const unsigned t = (unsigned)((na + 31) / 32);
+  symm_expand_kernel<T><<<dim3(t, t), 256, 0, s>>>(p.uplo, p.herm, na, (const T*)p.A, p.lda, (T*)W, ldw);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int launch_trsm(const TriProblem& p, cudaStream_t s) { return dispatch_tri<true>(p, s); }
+int launch_trmm(const TriProblem& p, cudaStream_t s) { return dispatch_tri<false>(p, s); }
+
+size_t symm_workspace_bytes(const SymmProblem& p) {
+  const int64_t na = p.left ? p.m : p.n;
+  const int64_t q = 32 / type_bytes(p.type) > 0 ? 32 / type_bytes(p.type) : 1;
+  const int64_t ldw = (na + q - 1) / q * q;
+  return (size_t)ldw * (size_t)na * (size_t)type_bytes(p.type);
+}
+
+// C = alpha * A * B + beta * C (left) or alpha * B * A + beta * C (right); A symmetric / Hermitian, one triangle stored
+int launch_symm(const SymmProblem& p, cudaStream_t s, void* workspace) {
+  if (p.m <= 0 || p.n <= 0) return 0;
+  const int64_t na = p.left ? p.m : p.n;
+  const int64_t q = 32 / type_bytes(p.type) > 0 ? 32 / type_bytes(p.type) : 1;
+  const int64_t ldw = (na + q - 1) / q * q;
+  int e;
+  switch (p.type) {
+    case TY_S: e = expand_typed<float>(p, na, workspace, ldw, s); break;
+    case TY_D: e = expand_typed<double>(p, na, workspace, ldw, s); break;
+    case TY_C: e = expand_typed<float2>(p, na, workspace, ldw, s); break;
+    default: e = expand_typed<double2>(p, na, workspace, ldw, s); break;
+  }
+  if (e) return e;
+  GemmProblem g;
+  g.type = p.type; g.opa = OP_N; g.opb = OP_N; g.m = p.m; g.n = p.n; g.k = na;
+  g.alpha[0] = p.alpha[0]; g.alpha[1] = p.alpha[1]; g.beta[0] = p.beta[0]; g.beta[1] = p.beta[1];
+  if (p.left) { g.A = workspace; g.lda = ldw; g.B = p.B; g.ldb = p.ldb; }
+  else { g.A = p.B; g.lda = p.ldb; g.B = workspace; g.ldb = ldw; }
+  g.C = p.C; g.ldc = p.ldc;
+  return run_gemm_device(g, s, B200BLAS_AUTO);
+}
+
+}  // namespace b200

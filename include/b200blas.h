@@ -57,6 +57,56 @@ int cherk_(const char* uplo, const char* trans, const int* n, const int* k, cons
            const int* lda, const float* beta, float* c, const int* ldc);   /* blas/complex_single.cpp via level3_impl.h:564 */
 int zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a,
            const int* lda, const double* beta, double* c, const int* ldc); /* blas/complex_double.cpp via level3_impl.h:564 */
+/* The remaining level-3 routines, composites of the same kernels -- see eigen_b200/csrc/tri.cu.
+ * ?trsm_: B := alpha * inv(op(A)) * B (side L) or alpha * B * inv(op(A)) (side R), A triangular; blas/level3_impl.h:78-178.
+ * ?trmm_: B := alpha * op(A) * B or alpha * B * op(A); blas/level3_impl.h:183-284 (returns 1 like the reference).
+ *   info 1 bad side | 2 bad uplo | 3 bad transa | 4 bad diag | 5 m<0 | 6 n<0 | 9 lda<max(1, side L ? m : n) | 11 ldb<max(1,m). */
+int strsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const float* alpha, const float* a, const int* lda, float* b, const int* ldb);
+int dtrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const double* alpha, const double* a, const int* lda, double* b, const int* ldb);
+int ctrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const float* alpha, const float* a, const int* lda, float* b, const int* ldb);
+int ztrsm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const double* alpha, const double* a, const int* lda, double* b, const int* ldb);
+int strmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const float* alpha, const float* a, const int* lda, float* b, const int* ldb);
+int dtrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const double* alpha, const double* a, const int* lda, double* b, const int* ldb);
+int ctrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const float* alpha, const float* a, const int* lda, float* b, const int* ldb);
+int ztrmm_(const char* side, const char* uplo, const char* transa, const char* diag, const int* m, const int* n,
+           const double* alpha, const double* a, const int* lda, double* b, const int* ldb);
+/* ?symm_ / ?hemm_: C := alpha * A * B + beta * C (side L) or alpha * B * A + beta * C (side R), A symmetric / Hermitian with
+ *   only its `uplo` triangle referenced; blas/level3_impl.h:287-355, :505-562.
+ *   info 1 bad side | 2 bad uplo | 3 m<0 | 4 n<0 | 7 lda<max(1, side L ? m : n) | 9 ldb<max(1,m) | 12 ldc<max(1,m).
+ * ?syr2k_ / ?her2k_: C.tri := alpha * op(A) op(B)^T + alpha * op(B) op(A)^T + beta * C.tri (her2k: ^H, conj(alpha) on the
+ *   second term, REAL beta, real diagonal); blas/level3_impl.h:437-503, :631-700.
+ *   info 1 bad uplo | 2 bad trans | 3 n<0 | 4 k<0 | 7 lda | 9 ldb | 12 ldc. */
+int ssymm_(const char* side, const char* uplo, const int* m, const int* n, const float* alpha, const float* a, const int* lda,
+            const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+int dsymm_(const char* side, const char* uplo, const int* m, const int* n, const double* alpha, const double* a, const int* lda,
+            const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+int csymm_(const char* side, const char* uplo, const int* m, const int* n, const float* alpha, const float* a, const int* lda,
+            const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+int zsymm_(const char* side, const char* uplo, const int* m, const int* n, const double* alpha, const double* a, const int* lda,
+            const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+int chemm_(const char* side, const char* uplo, const int* m, const int* n, const float* alpha, const float* a, const int* lda,
+            const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+int zhemm_(const char* side, const char* uplo, const int* m, const int* n, const double* alpha, const double* a, const int* lda,
+            const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+int ssyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
+            const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+int dsyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda,
+            const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+int csyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
+            const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+int zsyr2k_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda,
+            const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+int cher2k_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
+            const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
+int zher2k_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda,
+            const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
 /* Weak default prints "Eigen BLAS ERROR #<info>: <name>" like blas/xerbla.cpp:15-19; applications and testers
  * override it by defining their own xerbla_. */
 int xerbla_(const char* name, int* info, int len);

@@ -65,6 +65,15 @@ int oracle_csyrk_(const char* uplo, const char* trans, const int* n, const int* 
 int oracle_zsyrk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* beta, double* c, const int* ldc);
 int oracle_cherk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda, const float* beta, float* c, const int* ldc);
 int oracle_zherk_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda, const double* beta, double* c, const int* ldc);
+/* ---- trsm / trmm / symm / hemm / syr2k / her2k, blas/level3_impl.h:78-355,437-562,631-700 -- oracle/level3_port.c ---- */
+#define ORACLE_DECL_TRI(NAME, R) int NAME(const char* side, const char* uplo, const char* opa, const char* diag, const int* m, const int* n, const R* alpha, const R* a, const int* lda, R* b, const int* ldb);
+ORACLE_DECL_TRI(oracle_strsm_, float) ORACLE_DECL_TRI(oracle_dtrsm_, double) ORACLE_DECL_TRI(oracle_ctrsm_, float) ORACLE_DECL_TRI(oracle_ztrsm_, double)
+ORACLE_DECL_TRI(oracle_strmm_, float) ORACLE_DECL_TRI(oracle_dtrmm_, double) ORACLE_DECL_TRI(oracle_ctrmm_, float) ORACLE_DECL_TRI(oracle_ztrmm_, double)
+#define ORACLE_DECL_ABC(NAME, R) int NAME(const char* c1, const char* c2, const int* d1, const int* d2, const R* alpha, const R* a, const int* lda, const R* b, const int* ldb, const R* beta, R* c, const int* ldc);
+ORACLE_DECL_ABC(oracle_ssymm_, float) ORACLE_DECL_ABC(oracle_dsymm_, double) ORACLE_DECL_ABC(oracle_csymm_, float) ORACLE_DECL_ABC(oracle_zsymm_, double)
+ORACLE_DECL_ABC(oracle_chemm_, float) ORACLE_DECL_ABC(oracle_zhemm_, double)
+ORACLE_DECL_ABC(oracle_ssyr2k_, float) ORACLE_DECL_ABC(oracle_dsyr2k_, double) ORACLE_DECL_ABC(oracle_csyr2k_, float) ORACLE_DECL_ABC(oracle_zsyr2k_, double)
+ORACLE_DECL_ABC(oracle_cher2k_, float) ORACLE_DECL_ABC(oracle_zher2k_, double)
 void oracle_xerbla_expect(const char* name6, int infot);
 int oracle_xerbla_result(void);
 

@@ -26,6 +26,11 @@ _cp = C.c_char_p
 GEMM_ARGTYPES = [_cp, _cp, _ip, _ip, _ip, _vp, _vp, _ip, _vp, _ip, _vp, _vp, _ip]
 RANKK_ARGTYPES = [_cp, _cp, _ip, _ip, _vp, _vp, _ip, _vp, _vp, _ip]
 RANKK_NAMES = ["ssyrk_", "dsyrk_", "csyrk_", "zsyrk_", "cherk_", "zherk_"]
+TRI_ARGTYPES = [_cp, _cp, _cp, _cp, _ip, _ip, _vp, _vp, _ip, _vp, _ip]
+TRI_NAMES = [t + r for r in ("trsm_", "trmm_") for t in "sdcz"]
+ABC_ARGTYPES = [_cp, _cp, _ip, _ip, _vp, _vp, _ip, _vp, _ip, _vp, _vp, _ip]
+SYMM_NAMES = ["ssymm_", "dsymm_", "csymm_", "zsymm_", "chemm_", "zhemm_"]
+R2K_NAMES = ["ssyr2k_", "dsyr2k_", "csyr2k_", "zsyr2k_", "cher2k_", "zher2k_"]
 
 
 class Blat3Report(C.Structure):
@@ -35,10 +40,21 @@ class Blat3Report(C.Structure):
 
 def _build_port():
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gebp_port.c", "gebp_impl.h", "hp_ref.c", "blat3_port.c", "rankk_port.c", "oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gebp_port.c", "gebp_impl.h", "hp_ref.c", "blat3_port.c", "rankk_port.c", "level3_port.c", "oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "port"], stdout=subprocess.DEVNULL)
     return so
+
+
+def _bind_level3(lib, prefix):
+    for nm in TRI_NAMES:
+        f = getattr(lib, prefix + nm)
+        f.argtypes = TRI_ARGTYPES
+        f.restype = _i
+    for nm in SYMM_NAMES + R2K_NAMES:
+        f = getattr(lib, prefix + nm)
+        f.argtypes = ABC_ARGTYPES
+        f.restype = _i
 
 
 _port = None
@@ -59,6 +75,7 @@ def port():
             f = getattr(lib, "oracle_" + nm)
             f.argtypes = RANKK_ARGTYPES
             f.restype = _i
+        _bind_level3(lib, "oracle_")
         lib.oracle_xerbla_expect.argtypes = [_cp, _i]
         lib.oracle_xerbla_result.restype = _i
         lib.oracle_gemm_omp.argtypes = [_i, C.c_char, C.c_char, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i]
@@ -99,6 +116,7 @@ def ref_blas():
             f = getattr(lib, nm)
             f.argtypes = RANKK_ARGTYPES
             f.restype = _i
+        _bind_level3(lib, "")
         _ref_blas = lib
     return _ref_blas
 
@@ -198,3 +216,57 @@ def hp_rankk(name, uplo, trans, n, k, alpha, a, lda, beta, c, ldc):
 def tri_mask(n, uplo):
     i, j = np.indices((n, n))
     return (i <= j) if uplo in "Uu" else (i >= j)
+
+
+def call_tri(fn, name, side, uplo, trans, diag, m, n, alpha, a, lda, b, ldb):
+    """Call an F77-ABI ?trsm_/?trmm_."""
+    dt = NP_DTYPE[name[0]]
+    al = np.array([alpha], dtype=dt)
+    ints = [C.c_int(v) for v in (m, n, lda, ldb)]
+    return fn(side.encode(), uplo.encode(), trans.encode(), diag.encode(), C.byref(ints[0]), C.byref(ints[1]), _ptr(al), _ptr(a),
+              C.byref(ints[2]), _ptr(b), C.byref(ints[3]))
+
+
+def call_abc(fn, name, c1, c2, d1, d2, alpha, a, lda, b, ldb, beta, c, ldc):
+    """Call an F77-ABI ?symm_/?hemm_ (c1 = side, c2 = uplo, d1 = m, d2 = n) or ?syr2k_/?her2k_ (uplo, trans, n, k);
+    her2k takes a REAL beta."""
+    t = name[0]
+    dt = NP_DTYPE[t]
+    rdt = np.float32 if t in "sc" else np.float64
+    al = np.array([alpha], dtype=dt)
+    be = np.array([beta], dtype=rdt if "her2k" in name else dt)
+    ints = [C.c_int(v) for v in (d1, d2, lda, ldb, ldc)]
+    return fn(c1.encode(), c2.encode(), C.byref(ints[0]), C.byref(ints[1]), _ptr(al), _ptr(a), C.byref(ints[2]), _ptr(b),
+              C.byref(ints[3]), _ptr(be), _ptr(c), C.byref(ints[4]))
+
+
+def dense_triangular(a, n, uplo, diag):
+    """The n x n triangular matrix ?trsm_/?trmm_ see in `a` (other triangle zero, unit diagonal if diag == 'U')."""
+    t = np.array(a[:n, :n], order="F")
+    t = np.triu(t) if uplo in "Uu" else np.tril(t)
+    if diag in "Uu":
+        np.fill_diagonal(t, 1)
+    return np.asfortranarray(t)
+
+
+def dense_symmetric(a, n, uplo, herm):
+    """The n x n symmetric / Hermitian matrix ?symm_/?hemm_ see in the `uplo` triangle of `a`."""
+    t = np.array(a[:n, :n], order="F")
+    strict = np.triu(t, 1) if uplo in "Uu" else np.tril(t, -1)
+    d = np.diagonal(t).copy()
+    if herm:
+        d = d.real.astype(t.dtype)
+    full = strict + (strict.conj().T if herm else strict.T) + np.diag(d)
+    return np.asfortranarray(full.astype(t.dtype))
+
+
+def make_triangular(rng, t, n, ld, scale=None):
+    """A well-conditioned random triangular operand: off-diagonal uniform[-1,1] * scale, |diagonal| in [1, 2]
+    (the netlib generator also shifts the diagonal, dblat3.f DMAKE); both triangles are filled."""
+    scale = (2.0 / max(n, 2)) if scale is None else scale
+    a = rand_matrix(rng, t, n, n, ld=ld)
+    a[:n] = a[:n] * np.asarray(scale, dtype=a.real.dtype)
+    d = np.diagonal(a[:n]).copy()
+    d = np.where(np.abs(d) > 0, d / np.maximum(np.abs(d), 1e-30), 1) * (1 + rng.uniform(0, 1, size=n))
+    a[np.arange(n), np.arange(n)] = d.astype(a.dtype)
+    return a

@@ -18,7 +18,8 @@ def test_header_symbols_exported():
     hdr = open(os.path.join(ROOT, "include", "b200blas.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = set(re.findall(r"\b([a-z_0-9]+_?)\s*\(", hdr)) - {"defined"}
-    declared = {d for d in declared if d.endswith(("gemm_", "syrk_", "herk_")) or d.startswith("b200blas_") or d == "xerbla_"}
+    blas3 = ("gemm_", "syrk_", "herk_", "trsm_", "trmm_", "symm_", "hemm_", "syr2k_", "her2k_")
+    declared = {d for d in declared if (d.endswith(blas3) and len(d) <= 7) or d.startswith("b200blas_") or d == "xerbla_"}
     assert declared == set(eigen_b200.EXPORTS), declared ^ set(eigen_b200.EXPORTS)
     L = eigen_b200.lib()
     for name in declared:
@@ -82,3 +83,20 @@ def test_rankk_error_exits_without_gpu(name):
         assert P.oracle_xerbla_result() == 1, (name, info)
     # n == 0 returns before anything is touched
     assert oa.call_rankk(getattr(L, name), name, "U", "N", 0, 3, 1.0, a, 4, 0.0, c, 4) == 0
+
+
+@pytest.mark.parametrize("name", oa.TRI_NAMES + oa.SYMM_NAMES + oa.R2K_NAMES)
+def test_level3_error_exits_without_gpu(name):
+    """?TRSM ?TRMM ?SYMM ?HEMM ?SYR2K ?HER2K blocks of xCHKE -- argument checking precedes any CUDA work; empty results
+    return before anything is touched, with the reference's return values (blas/level3_impl.h:160,265,318,470)."""
+    import level3_cases as lc
+    L = eigen_b200.lib()
+    lc.run_error_exits(oa.port(), getattr(L, name), name)
+    t = name[0]
+    z = np.zeros((4, 4), dtype=oa.NP_DTYPE[t], order="F")
+    if name[1:] in ("trsm_", "trmm_"):
+        assert oa.call_tri(getattr(L, name), name, "L", "U", "N", "N", 0, 3, 1.0, z, 4, z, 4) == (1 if "trmm" in name else 0)
+    elif name[1:] in ("symm_", "hemm_"):
+        assert oa.call_abc(getattr(L, name), name, "L", "U", 0, 3, 1.0, z, 4, z, 4, 0.0, z, 4) == 1
+    else:
+        assert oa.call_abc(getattr(L, name), name, "U", "N", 0, 3, 1.0, z, 4, z, 4, 0.0, z, 4) == 0
