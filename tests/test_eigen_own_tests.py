@@ -1,6 +1,9 @@
-"""The reference's OWN product unit tests (test/product_{large,extra,small,notemporary}.cpp), compiled unmodified
+"""The reference's OWN unit tests (test/product_{large,extra,small,trsolve,syrk}.cpp, cholesky.cpp, lu.cpp), compiled unmodified
 with -DEIGEN_USE_BLAS by oracle/Makefile (target eigen_tests) and linked against libb200blas.so: every Eigen
-`A*B` in them reaches our ?gemm_ through GeneralMatrixMatrix_BLAS.h:103.  Needs a B200 (the binaries abort through
+`A*B` in them reaches our ?gemm_ through GeneralMatrixMatrix_BLAS.h:103, every triangular solve our ?trsm_
+(TriangularSolverMatrix_BLAS.h:41-157) and every triangular product our ?trmm_ (TriangularMatrixMatrix_BLAS.h).
+(test/product_symm.cpp does not compile in this snapshot with g++ 13 -- SelfAdjointView static assertion -- and
+test/product_trmm.cpp binds no BLAS symbol, so neither is in the list.)  Needs a B200 (the binaries abort through
 xerbla_ info=-1 otherwise: there is no CPU fallback)."""
 import os
 import subprocess
@@ -30,3 +33,9 @@ def _run(name, variant, seed):
 @pytest.mark.parametrize("name", ["product_large", "product_extra", "product_small"])
 def test_eigen_product_tests_pass_on_the_gpu_library(name, variant):
     _run(name, variant, 12345)
+
+
+@pytest.mark.parametrize("name", ["product_trsolve", "cholesky", "lu", "product_syrk"])
+def test_eigen_solver_tests_pass_on_the_gpu_library(name):
+    """Binaries import ?trsm_/?trmm_/?gemm_ from libb200blas.so (nm -D); ?gemv_/?trmv_ come from the reference blas."""
+    _run(name, "auto", 4242)
