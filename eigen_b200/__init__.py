@@ -21,7 +21,8 @@ VARIANT = {"auto": 0, "simt": 1, "dmma": 2, "tf32x3": 3}
 # every symbol include/b200blas.h declares
 EXPORTS = ["sgemm_", "dgemm_", "cgemm_", "zgemm_", "ssyrk_", "dsyrk_", "csyrk_", "zsyrk_", "cherk_", "zherk_",
            "strsm_", "dtrsm_", "ctrsm_", "ztrsm_", "strmm_", "dtrmm_", "ctrmm_", "ztrmm_", "ssymm_", "dsymm_", "csymm_", "zsymm_",
-           "chemm_", "zhemm_", "ssyr2k_", "dsyr2k_", "csyr2k_", "zsyr2k_", "cher2k_", "zher2k_", "xerbla_", "b200blas_gemm_dev", "b200blas_version",
+           "chemm_", "zhemm_", "ssyr2k_", "dsyr2k_", "csyr2k_", "zsyr2k_", "cher2k_", "zher2k_",
+           "spotrf_", "dpotrf_", "cpotrf_", "zpotrf_", "sgetrf_", "dgetrf_", "cgetrf_", "zgetrf_", "xerbla_", "b200blas_gemm_dev", "b200blas_version",
            "b200blas_device_ok", "b200blas_last_error", "b200blas_last_variant", "b200blas_kernel_launches",
            "b200blas_set_variant", "b200blas_last_transfer", "b200blas_release", "b200blas_pipe_peak"]
 
@@ -74,6 +75,13 @@ def lib():
             f = getattr(L, name)
             f.argtypes = [cp, cp, ip, ip, vp, vp, ip, vp, ip, vp, vp, ip]
             f.restype = i
+    for t in "sdcz":
+        f = getattr(L, t + "potrf_")
+        f.argtypes = [cp, ip, vp, ip, ip]
+        f.restype = i
+        f = getattr(L, t + "getrf_")
+        f.argtypes = [ip, ip, vp, ip, ip, ip]
+        f.restype = i
     L.b200blas_gemm_dev.argtypes = [i, C.c_char, C.c_char, i, i, i, vp, vp, C.c_int64, vp, C.c_int64, vp, vp,
                                     C.c_int64, vp, i]
     L.b200blas_gemm_dev.restype = i

@@ -57,6 +57,12 @@ struct SymmProblem {
   void* C; int64_t ldc;
 };
 
+// In-place Cholesky A = L L^H / U^H U (?potrf_, lapack/cholesky.cpp:14-38) and LU with partial pivoting P A = L U (?getrf_,
+// lapack/lu.cpp:14-42) on device memory.  *dinfo must hold INT_MAX on entry; the kernels atomicMin the first failing
+// 1-based index into it.  dipiv receives min(m, n) 1-based row numbers.
+struct PotrfProblem { int type; int uplo; int64_t n; void* A; int64_t lda; int* dinfo; };
+struct GetrfProblem { int type; int64_t m, n; void* A; int64_t lda; int* dipiv; int* dinfo; };
+
 static inline int type_bytes(int t) { return t == TY_S ? 4 : t == TY_Z ? 16 : 8; }
 
 // kernel launchers (one translation unit each); return cudaError_t as int, bump the launch counter themselves
@@ -73,6 +79,8 @@ int launch_trsm(const TriProblem& p, cudaStream_t s);   // tri.cu
 int launch_trmm(const TriProblem& p, cudaStream_t s);
 size_t symm_workspace_bytes(const SymmProblem& p);
 int launch_symm(const SymmProblem& p, cudaStream_t s, void* workspace);
+int launch_potrf(const PotrfProblem& p, cudaStream_t s);   // lapack.cu
+int launch_getrf(const GetrfProblem& p, cudaStream_t s);
 
 void count_launch(int n = 1);
 void note_variant(const char* name);

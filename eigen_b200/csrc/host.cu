@@ -9,6 +9,7 @@
 // upload of slab j+1, the product on slab j and the download of slab j-1 overlap (the GPU analogue of the kc/nc
 // panel streaming of GeneralMatrixMatrix.h:155-198).  There is no CPU fallback.
 #include <atomic>
+#include <climits>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -946,6 +947,103 @@ static int r2k_entry(int type, bool her, const char* uplo, const char* op, const
   return (her || *pk == 0) ? 1 : 0;   // return values of level3_impl.h:470-471,502 / :672-673,699
 }
 
+
+// ---- ?potrf_ / ?getrf_: device-resident blocked factorizations -------------------------------------------
+// lapack/cholesky.cpp:14-38 and lapack/lu.cpp:14-42.  The matrix is uploaded once, factored in HBM by lapack.cu (no
+// per-block PCIe round trips, which is what makes config C5 PCIe-bound through the BLAS seam) and downloaded once.
+static const char* k_potrf_names[4] = {"SPOTRF", "DPOTRF", "CPOTRF", "ZPOTRF"};
+static const char* k_getrf_names[4] = {"SGETRF", "DGETRF", "CGETRF", "ZGETRF"};
+
+// small device scratch for info + pivots, stream-ordered
+struct DevInts {
+  int* p = nullptr; cudaStream_t s;
+  int alloc(size_t n, cudaStream_t st) { s = st; keep_pool_memory(); return (int)cudaMallocAsync((void**)&p, n * sizeof(int), st); }
+  ~DevInts() { if (p) cudaFreeAsync(p, s); }
+};
+
+static int potrf_entry(int type, const char* uplo, const int* pn, void* a, const int* plda, int* info) {
+  const int ul = uplo_of(*uplo);
+  *info = 0;
+  if (ul < 0) *info = -1;
+  else if (*pn < 0) *info = -2;
+  else if (*plda < std::max(1, *pn)) *info = -4;
+  if (*info != 0) { int e = -*info; return xerbla_(k_potrf_names[type], &e, 6); }
+  if (*pn == 0) return 0;
+  const int64_t n = *pn;
+  const size_t es = (size_t)type_bytes(type);
+  t_error[0] = 0;
+  int err = 0, hinfo = INT_MAX;
+  const bool dev_a = is_device_ptr(a);
+  std::unique_lock<std::mutex> lock(g_stage.mu, std::defer_lock);
+  Staging& st = g_stage;
+  cudaStream_t s = nullptr;
+  PotrfProblem p;
+  p.type = type; p.uplo = ul; p.n = n; p.A = a; p.lda = *plda;
+  int64_t dlda = 0;
+  if (!dev_a) {
+    lock.lock();
+    err = st.init();
+    t_h2d = t_d2h = 0;
+    if (!err) err = stage_in(st, 2, a, *plda, n, n, es, true, &dlda);
+    if (!err) err = inputs_ready(st);
+    s = st.s_comp;
+    p.A = st.dbuf[2]; p.lda = dlda;
+  }
+  DevInts di;
+  if (!err) err = di.alloc(1, s);
+  if (!err) err = (int)cudaMemcpyAsync(di.p, &hinfo, sizeof(int), cudaMemcpyHostToDevice, s);
+  if (!err) { p.dinfo = di.p; err = launch_potrf(p, s); }
+  if (!err) err = (int)cudaMemcpyAsync(&hinfo, di.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (!err) err = (int)cudaStreamSynchronize(s);
+  if (!err && !dev_a) {
+    err = ring_d2h_triangle(st.ring_out, (char*)a, (size_t)*plda * es, (const char*)st.dbuf[2], (size_t)dlda * es, (size_t)n, es, ul, st.s_out);
+    t_d2h += (uint64_t)n * (n + 1) / 2 * es;
+  }
+  if (err) { cudaDeviceSynchronize(); fail(err); int e = -1; *info = -1; return xerbla_(k_potrf_names[type], &e, 6); }
+  *info = (hinfo == INT_MAX) ? 0 : hinfo;   // index of the first non-positive pivot, 1-based (cholesky.cpp:34-35)
+  return 0;
+}
+
+static int getrf_entry(int type, const int* pm, const int* pn, void* a, const int* plda, int* ipiv, int* info) {
+  *info = 0;
+  if (*pm < 0) *info = -1;
+  else if (*pn < 0) *info = -2;
+  else if (*plda < std::max(1, *pm)) *info = -4;
+  if (*info != 0) { int e = -*info; return xerbla_(k_getrf_names[type], &e, 6); }
+  if (*pm == 0 || *pn == 0) return 0;
+  const int64_t m = *pm, n = *pn, size = std::min(m, n);
+  const size_t es = (size_t)type_bytes(type);
+  t_error[0] = 0;
+  int err = 0, hinfo = INT_MAX;
+  const bool dev_a = is_device_ptr(a);
+  std::unique_lock<std::mutex> lock(g_stage.mu, std::defer_lock);
+  Staging& st = g_stage;
+  cudaStream_t s = nullptr;
+  GetrfProblem p;
+  p.type = type; p.m = m; p.n = n; p.A = a; p.lda = *plda;
+  int64_t dlda = 0;
+  if (!dev_a) {
+    lock.lock();
+    err = st.init();
+    t_h2d = t_d2h = 0;
+    if (!err) err = stage_in(st, 2, a, *plda, m, n, es, true, &dlda);
+    if (!err) err = inputs_ready(st);
+    s = st.s_comp;
+    p.A = st.dbuf[2]; p.lda = dlda;
+  }
+  DevInts di;
+  if (!err) err = di.alloc((size_t)size + 1, s);
+  if (!err) err = (int)cudaMemcpyAsync(di.p, &hinfo, sizeof(int), cudaMemcpyHostToDevice, s);
+  if (!err) { p.dinfo = di.p; p.dipiv = di.p + 1; err = launch_getrf(p, s); }
+  if (!err) err = (int)cudaMemcpyAsync(&hinfo, di.p, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (!err) err = (int)cudaMemcpyAsync(ipiv, di.p + 1, (size_t)size * sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (!err) err = (int)cudaStreamSynchronize(s);
+  if (!err && !dev_a) err = stage_out(st, 2, a, *plda, m, n, es, dlda);
+  if (err) { cudaDeviceSynchronize(); fail(err); int e = -1; *info = -1; return xerbla_(k_getrf_names[type], &e, 6); }
+  *info = (hinfo == INT_MAX) ? 0 : hinfo;   // first exactly-zero pivot, 1-based (lu.cpp:38-39)
+  return 0;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -1000,6 +1098,15 @@ B200_SYMM(chemm_, TY_C, true, float) B200_SYMM(zhemm_, TY_Z, true, double)
 B200_R2K(ssyr2k_, TY_S, false, float) B200_R2K(dsyr2k_, TY_D, false, double) B200_R2K(csyr2k_, TY_C, false, float) B200_R2K(zsyr2k_, TY_Z, false, double)
 B200_R2K(cher2k_, TY_C, true, float) B200_R2K(zher2k_, TY_Z, true, double)
 #undef B200_R2K
+
+int spotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info) { return potrf_entry(TY_S, uplo, n, a, lda, info); }
+int dpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info) { return potrf_entry(TY_D, uplo, n, a, lda, info); }
+int cpotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info) { return potrf_entry(TY_C, uplo, n, a, lda, info); }
+int zpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info) { return potrf_entry(TY_Z, uplo, n, a, lda, info); }
+int sgetrf_(const int* m, const int* n, float* a, const int* lda, int* ipiv, int* info) { return getrf_entry(TY_S, m, n, a, lda, ipiv, info); }
+int dgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info) { return getrf_entry(TY_D, m, n, a, lda, ipiv, info); }
+int cgetrf_(const int* m, const int* n, float* a, const int* lda, int* ipiv, int* info) { return getrf_entry(TY_C, m, n, a, lda, ipiv, info); }
+int zgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info) { return getrf_entry(TY_Z, m, n, a, lda, ipiv, info); }
 
 int ssyrk_(const char* uplo, const char* trans, const int* n, const int* k, const float* alpha, const float* a, const int* lda,
            const float* beta, float* c, const int* ldc) { return rankk_entry(TY_S, false, uplo, trans, n, k, alpha, a, lda, beta, c, ldc); }

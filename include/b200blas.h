@@ -107,6 +107,22 @@ int cher2k_(const char* uplo, const char* trans, const int* n, const int* k, con
             const float* b, const int* ldb, const float* beta, float* c, const int* ldc);
 int zher2k_(const char* uplo, const char* trans, const int* n, const int* k, const double* alpha, const double* a, const int* lda,
             const double* b, const int* ldb, const double* beta, double* c, const int* ldc);
+/* Device-resident blocked factorizations -- eigen_b200/csrc/lapack.cu.  LAPACK F77 ABI of the reference's
+ * lapack/ module: the matrix is uploaded once (or already lives in HBM: device pointers are accepted for `a`; ipiv and
+ * info are always HOST pointers), factored in place, and brought back once.
+ * ?potrf_: A = L L^H (uplo 'L') or U^H U (uplo 'U'); only the `uplo` triangle is referenced / overwritten;
+ *   info -1 bad uplo | -2 n<0 | -4 lda<max(1,n) (-> xerbla_("xPOTRF", &(-info), 6)); info = k > 0: the leading minor of
+ *   order k is not positive definite.  lapack/cholesky.cpp:14-38, Eigen/src/Cholesky/LLT.h:299-360.
+ * ?getrf_: P A = L U with partial pivoting, ipiv 1-based; info -1 m<0 | -2 n<0 | -4 lda<max(1,m); info = k > 0: U(k,k) is
+ *   exactly zero (the factorization is completed).  lapack/lu.cpp:14-42, Eigen/src/LU/PartialPivLU.h:361-496. */
+int spotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info);
+int dpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+int cpotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info);
+int zpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+int sgetrf_(const int* m, const int* n, float* a, const int* lda, int* ipiv, int* info);
+int dgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
+int cgetrf_(const int* m, const int* n, float* a, const int* lda, int* ipiv, int* info);
+int zgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
 /* Weak default prints "Eigen BLAS ERROR #<info>: <name>" like blas/xerbla.cpp:15-19; applications and testers
  * override it by defining their own xerbla_. */
 int xerbla_(const char* name, int* info, int len);

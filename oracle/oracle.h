@@ -74,6 +74,15 @@ ORACLE_DECL_ABC(oracle_ssymm_, float) ORACLE_DECL_ABC(oracle_dsymm_, double) ORA
 ORACLE_DECL_ABC(oracle_chemm_, float) ORACLE_DECL_ABC(oracle_zhemm_, double)
 ORACLE_DECL_ABC(oracle_ssyr2k_, float) ORACLE_DECL_ABC(oracle_dsyr2k_, double) ORACLE_DECL_ABC(oracle_csyr2k_, float) ORACLE_DECL_ABC(oracle_zsyr2k_, double)
 ORACLE_DECL_ABC(oracle_cher2k_, float) ORACLE_DECL_ABC(oracle_zher2k_, double)
+/* ---- potrf / getrf, lapack/cholesky.cpp:14-38, lapack/lu.cpp:14-42 -- oracle/lapack_port.c ---------------------- */
+int oracle_spotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info);
+int oracle_dpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+int oracle_cpotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info);
+int oracle_zpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
+int oracle_sgetrf_(const int* m, const int* n, float* a, const int* lda, int* ipiv, int* info);
+int oracle_dgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
+int oracle_cgetrf_(const int* m, const int* n, float* a, const int* lda, int* ipiv, int* info);
+int oracle_zgetrf_(const int* m, const int* n, double* a, const int* lda, int* ipiv, int* info);
 void oracle_xerbla_expect(const char* name6, int infot);
 int oracle_xerbla_result(void);
 

@@ -40,10 +40,59 @@ class Blat3Report(C.Structure):
 
 def _build_port():
     so = os.path.join(ORACLE_DIR, "liboracle.so")
-    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gebp_port.c", "gebp_impl.h", "hp_ref.c", "blat3_port.c", "rankk_port.c", "level3_port.c", "oracle.h")]
+    srcs = [os.path.join(ORACLE_DIR, f) for f in ("gebp_port.c", "gebp_impl.h", "hp_ref.c", "blat3_port.c", "rankk_port.c", "level3_port.c", "lapack_port.c", "oracle.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", ORACLE_DIR, "port"], stdout=subprocess.DEVNULL)
     return so
+
+
+POTRF_ARGTYPES = [_cp, _ip, _vp, _ip, _ip]
+GETRF_ARGTYPES = [_ip, _ip, _vp, _ip, _ip, _ip]
+
+
+def _bind_lapack(lib, prefix):
+    for t in "sdcz":
+        f = getattr(lib, prefix + t + "potrf_")
+        f.argtypes = POTRF_ARGTYPES
+        f.restype = _i
+        f = getattr(lib, prefix + t + "getrf_")
+        f.argtypes = GETRF_ARGTYPES
+        f.restype = _i
+
+
+_ref_lapack = None
+
+
+def have_ref_lapack():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libeigen_lapack_ref.so"))
+
+
+def ref_lapack():
+    """The reference's own ?potrf_/?getrf_ (lapack/cholesky.cpp, lapack/lu.cpp via oracle/ref_lapack_shim.cpp)."""
+    global _ref_lapack
+    if _ref_lapack is None:
+        port()
+        lib = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libeigen_lapack_ref.so"), mode=C.RTLD_LOCAL)
+        _bind_lapack(lib, "")
+        _ref_lapack = lib
+    return _ref_lapack
+
+
+def call_potrf(fn, uplo, n, a, lda):
+    """F77 ?potrf_; returns info."""
+    info = C.c_int(12345)
+    ints = [C.c_int(n), C.c_int(lda)]
+    fn(uplo.encode(), C.byref(ints[0]), _ptr(a), C.byref(ints[1]), C.byref(info))
+    return info.value
+
+
+def call_getrf(fn, m, n, a, lda):
+    """F77 ?getrf_; returns (ipiv (1-based, length min(m,n)), info)."""
+    info = C.c_int(12345)
+    ipiv = np.zeros(max(min(m, n), 1), dtype=np.int32)
+    ints = [C.c_int(m), C.c_int(n), C.c_int(lda)]
+    fn(C.byref(ints[0]), C.byref(ints[1]), _ptr(a), C.byref(ints[2]), ipiv.ctypes.data_as(_ip), C.byref(info))
+    return ipiv[:min(m, n)], info.value
 
 
 def _bind_level3(lib, prefix):
@@ -76,6 +125,7 @@ def port():
             f.argtypes = RANKK_ARGTYPES
             f.restype = _i
         _bind_level3(lib, "oracle_")
+        _bind_lapack(lib, "oracle_")
         lib.oracle_xerbla_expect.argtypes = [_cp, _i]
         lib.oracle_xerbla_result.restype = _i
         lib.oracle_gemm_omp.argtypes = [_i, C.c_char, C.c_char, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i]
