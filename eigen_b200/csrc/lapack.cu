@@ -58,8 +58,15 @@ __global__ void __launch_bounds__(32) potf2_leaf_kernel(int upper, int d, int64_
   using R = typename Sc<T>::real;
   __shared__ T S[NB][NB + 1];
   const int lane = threadIdx.x;
-  for (int j = 0; j < d; ++j)
-    if (lane < d && lane >= j) S[lane][j] = upper ? Sc<T>::conj(A[j + (int64_t)lane * lda]) : A[lane + (int64_t)j * lda];
+  {
+    T v[NB];   // the lane's whole row in flight at once
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      v[j] = (j < d && lane < d && lane >= j) ? (upper ? A[j + (int64_t)lane * lda] : A[lane + (int64_t)j * lda]) : Sc<T>::zero();
+#pragma unroll
+    for (int j = 0; j < NB; ++j)
+      if (j < d && lane < d && lane >= j) S[lane][j] = upper ? Sc<T>::conj(v[j]) : v[j];
+  }
   __syncwarp();
   for (int k = 0; k < d; ++k) {
     const R x = sc_real<T>(S[k][k]);
@@ -148,7 +155,7 @@ getf2_panel_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, i
   constexpr int LDS = NBP + 1;
   __shared__ T prow[NBP], krow[NBP];
   __shared__ double red_score[8];
-  __shared__ int red_row[8];
+  __shared__ int red_row[8], red_w[8];
   __shared__ double win_score;
   __shared__ int win_row;
   using Cand = PanelCand<T, NBP>;
@@ -166,8 +173,14 @@ getf2_panel_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, i
   }
   const int64_t r0 = (int64_t)cta * rows_per_cta;
   const int R = (int)max((int64_t)0, min((int64_t)rows_per_cta, mrows - r0));
-  for (int c = 0; c < nb; ++c)
-    for (int r = tid; r < R; r += 256) slab[r * LDS + c] = A[(r0 + r) + (int64_t)c * lda];
+  for (int r = tid; r < R; r += 256)
+    for (int c0 = 0; c0 < nb; c0 += 8) {
+      T v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (c0 + q < nb) ? A[(r0 + r) + (int64_t)(c0 + q) * lda] : Sc<T>::zero();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (c0 + q < nb) slab[r * LDS + c0 + q] = v[q];
+    }
   __syncthreads();
   const int steps = (int)min((int64_t)nb, mrows);
   for (int k = 0; k < steps; ++k) {
@@ -204,14 +217,16 @@ getf2_panel_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, i
     }
     // 3. one grid-wide barrier per column
     grid_barrier(counter, (unsigned)(k + 1) * (unsigned)G);
-    // 4. every CTA reduces the published candidates (identically) and fetches the two rows
-    if (tid < 32) {
+    // 4. every CTA reduces the published candidates (identically): one L2 load per thread, then a block reduction;
+    //    the winner's row and row k are fetched by the first warp
+    {
       double gb = -1.0;
       int grow = INT_MAX, gw = -1;
-      for (int w = tid; w < G; w += 32) {
-        const double s2 = __ldcg(&cands[par][w].score);   // L2 reads: the data was written by other SMs
-        const int r2 = __ldcg(&cands[par][w].row);
-        if (s2 > gb || (s2 == gb && r2 < grow)) { gb = s2; grow = r2; gw = w; }
+      if (tid < G) {
+        gb = __ldcg(&cands[par][tid].score);   // L2 reads: the data was written by other SMs
+        grow = __ldcg(&cands[par][tid].row);
+        gw = tid;
+        if (!(gb >= 0.0)) { gb = -1.0; grow = INT_MAX; gw = -1; }
       }
       for (int off = 16; off > 0; off >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, gb, off);
@@ -219,9 +234,16 @@ getf2_panel_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, i
         const int ow = __shfl_xor_sync(0xffffffffu, gw, off);
         if (ob > gb || (ob == gb && orow < grow)) { gb = ob; grow = orow; gw = ow; }
       }
-      if (gw < 0) { gb = 0.0; grow = k; }   // a column of NaNs: no candidate compares greater; treated as a zero pivot
-      if (tid == 0) { win_score = gb; win_row = grow; }
-      if (tid < nb && gw >= 0) { prow[tid] = __ldcg(&cands[par][gw].vals[tid]); krow[tid] = __ldcg(&rowk[par][tid]); }
+      if ((tid & 31) == 0) { red_score[tid >> 5] = gb; red_row[tid >> 5] = grow; red_w[tid >> 5] = gw; }
+      __syncthreads();
+      if (tid < 32) {
+        gb = red_score[0]; grow = red_row[0]; gw = red_w[0];
+        for (int w = 1; w < 8; ++w)
+          if (red_score[w] > gb || (red_score[w] == gb && red_row[w] < grow)) { gb = red_score[w]; grow = red_row[w]; gw = red_w[w]; }
+        if (gw < 0) { gb = 0.0; grow = k; }   // a column of NaNs: no candidate compares greater; treated as a zero pivot
+        if (tid == 0) { win_score = gb; win_row = grow; }
+        if (tid < nb && gw >= 0) { prow[tid] = __ldcg(&cands[par][gw].vals[tid]); krow[tid] = __ldcg(&rowk[par][tid]); }
+      }
     }
     __syncthreads();
     const double gscore = win_score;
@@ -366,7 +388,7 @@ template <typename T>
 int launch_panel(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t nc, cudaStream_t s) {
   constexpr int NBP = Leaf<T>::NB;
   const int64_t mrows = p.m - j0;
-  int G = (int)std::min<int64_t>(cx.sms, (mrows + 63) / 64);
+  int G = (int)std::min<int64_t>(cx.sms, (mrows + 255) / 256);   // about one panel row per thread; G <= 256 (candidate reduce)
   if (G < 1) G = 1;
   int rows_per_cta = (int)((mrows + G - 1) / G);
   const size_t smem = (size_t)rows_per_cta * (NBP + 1) * sizeof(T);

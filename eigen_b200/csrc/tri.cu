@@ -25,30 +25,43 @@ namespace {
 // Entries outside the referenced triangle are zero, a unit diagonal is one, and rows/columns past nb are the identity,
 // so the fully unrolled NB-step recurrence is valid for every nb <= NB.  In SOLVE mode the diagonal holds reciprocals
 // (the reference multiplies by 1/diag as well, TriangularSolverMatrix.h:118-121).
+constexpr int LEAF_THREADS = 256;   // one right-hand-side vector per thread
+
 template <typename T, int NB, bool LOWER, bool SOLVE>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(LEAF_THREADS)
 tri_leaf_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrhs, const T* __restrict__ A, int64_t lda,
                 T* __restrict__ B, int64_t ldb) {
   __shared__ T S[NB][NB];
-  for (int idx = threadIdx.x; idx < NB * NB; idx += 64) {
-    const int i = idx % NB, j = idx / NB;
-    T v = (i == j) ? sc_one<T>() : Sc<T>::zero();
-    if (i < nb && j < nb) {
-      const bool swap = left ? (op != OP_N) : (op == OP_N);
+  {
+    // all loads of the block are issued before any is consumed (a load-per-iteration loop costs one DRAM latency each)
+    constexpr int PER = (NB * NB + LEAF_THREADS - 1) / LEAF_THREADS;
+    T vals[PER];
+    const bool swap = left ? (op != OP_N) : (op == OP_N);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int idx = threadIdx.x + q * LEAF_THREADS;
+      const int i = idx % NB, j = idx / NB;
       const int r = swap ? j : i, c = swap ? i : j;   // element of A
-      const bool referenced = (r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c);
+      const bool referenced = idx < NB * NB && i < nb && j < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
+      vals[q] = referenced ? A[r + c * lda] : ((i == j) ? sc_one<T>() : Sc<T>::zero());
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int idx = threadIdx.x + q * LEAF_THREADS;
+      if (idx >= NB * NB) continue;
+      const int i = idx % NB, j = idx / NB;
+      const int r = swap ? j : i, c = swap ? i : j;
+      const bool referenced = i < nb && j < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
+      T v = vals[q];
       if (referenced) {
-        v = A[r + c * lda];
         if (op == OP_C) v = Sc<T>::conj(v);
         if (SOLVE && r == c) v = sc_recip<T>(v);
-      } else if (r != c) {
-        v = Sc<T>::zero();
       }
+      S[i][j] = v;
     }
-    S[i][j] = v;
   }
   __syncthreads();
-  const int64_t v = (int64_t)blockIdx.x * 64 + threadIdx.x;
+  const int64_t v = (int64_t)blockIdx.x * LEAF_THREADS + threadIdx.x;
   if (v >= nrhs) return;
   T* bp = left ? B + v * ldb : B + v;
   const int64_t bs = left ? 1 : ldb;
@@ -155,11 +168,11 @@ int launch_leaf(const TriProblem& p, bool s_lower, int64_t d0, int nb, cudaStrea
   const T* A = (const T*)p.A + d0 + d0 * p.lda;
   T* B = p.left ? (T*)p.B + d0 : (T*)p.B + d0 * p.ldb;
   const int64_t nrhs = p.left ? p.n : p.m;
-  const unsigned grid = (unsigned)((nrhs + 63) / 64);
+  const unsigned grid = (unsigned)((nrhs + LEAF_THREADS - 1) / LEAF_THREADS);
   if (s_lower)
-    tri_leaf_kernel<T, NB, true, SOLVE><<<grid, 64, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+    tri_leaf_kernel<T, NB, true, SOLVE><<<grid, LEAF_THREADS, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
   else
-    tri_leaf_kernel<T, NB, false, SOLVE><<<grid, 64, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+    tri_leaf_kernel<T, NB, false, SOLVE><<<grid, LEAF_THREADS, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
   count_launch();
   return (int)cudaGetLastError();
 }
