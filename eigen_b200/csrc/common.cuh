@@ -1,6 +1,7 @@
 // eigen_b200/csrc/common.cuh -- shared declarations of libb200blas (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -89,6 +90,21 @@ void note_variant(const char* name);
   do {                                                       \
     const int _e = (int)(expr);                              \
     if (_e != 0) return _e;                                  \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a driver call of tens of microseconds: inside a chain of
+// thousands of small dependent launches (?trsm_ / ?potrf_ / ?getrf_) it would leave the GPU idle between kernels.
+// The attribute is per device, so each call site remembers the devices it has configured (one static mask per
+// template instantiation).
+#define B200_SET_MAX_DYN_SMEM_ONCE(kernel, bytes)                                                              \
+  do {                                                                                                          \
+    static std::atomic<uint64_t> _done{0};                                                                      \
+    int _dev = 0;                                                                                               \
+    B200_CUDA_TRY(cudaGetDevice(&_dev));                                                                        \
+    if (!((_done.load(std::memory_order_relaxed) >> (_dev & 63)) & 1ull)) {                                     \
+      B200_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+      _done.fetch_or(1ull << (_dev & 63), std::memory_order_relaxed);                                           \
+    }                                                                                                           \
   } while (0)
 
 // ---- device helpers ---------------------------------------------------------------------------------------

@@ -419,6 +419,11 @@ bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // prologue and epilogue bubbles (profiles/variant_sweep_r01.md: wins or ties against 128x128 / 1 CTA per SM).
 using CfgB = Cfg<128, 64, 32, 32, 2, 16, 4, false>;
 using CfgM = Cfg<128, 64, 32, 32, 2, 16, 4, true>;   // same tile, mbarrier pipeline (B200BLAS_DMMA_SYNC=mbar)
+// 64x32x16 tile, 8 warps of 16x16, 3 CTAs / SM: for products whose 128x64 tiling fills less than a third of the 296
+// CTA slots (the mid-size updates inside ?trsm_ / ?potrf_ / ?getrf_): a CTA's k-loop is bound by its own DMMA issue rate
+// (64 DMMA per warp and k-tile = 2048 cycles with two warps per sub-partition), so a quarter-size tile on four times as
+// many SMs finishes the same product up to 4x sooner.
+using CfgS = Cfg<64, 32, 16, 16, 3, 16, 4, true>;
 
 template <typename C, bool CPLX, int AMODE, int BMODE>
 int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
@@ -426,7 +431,7 @@ int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const Pa
   const int64_t tiles_m = (p.m * sc + C::BM - 1) / C::BM, tiles_n = (p.n * sc + C::BN - 1) / C::BN;
   const int64_t tiles = tiles_m * tiles_n;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
-  B200_CUDA_TRY(cudaFuncSetAttribute(dmma_gemm_kernel<C, CPLX, AMODE, BMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));   // per device and cheap: set on every launch
+  B200_SET_MAX_DYN_SMEM_ONCE((dmma_gemm_kernel<C, CPLX, AMODE, BMODE>), C::SMEM_BYTES);
   dmma_gemm_kernel<C, CPLX, AMODE, BMODE><<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(
       a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep, tiles_m, tiles_n);
   count_launch();
@@ -515,7 +520,12 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
     EpiParams e2 = ep;
     if (k0 > 0) { e2.beta[0] = 1.0; e2.beta[1] = 0.0; e2.beta_zero = 0; }
     int rc;
-    if (use_mbar()) {
+    static const int tile_env = [] { const char* e = getenv("B200BLAS_DMMA_TILE"); return !e ? 0 : (e[0] == 's' ? 1 : 2); }();
+    const int64_t big_tiles = ((q.m * sc + CfgM::BM - 1) / CfgM::BM) * ((q.n * sc + CfgM::BN - 1) / CfgM::BN);
+    if (tile_env == 1 || (tile_env == 0 && big_tiles <= 100)) {
+      note_variant(cplx ? "dmma_z_32x16x16_w8x8_3cta_mbar" : "dmma_d_64x32x16_w16x16_3cta_mbar");
+      rc = launch_modes<CfgS>(cplx, amode, bmode, q, s, a2, b2, e2);
+    } else if (use_mbar()) {
       note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta_mbar" : "dmma_d_128x64x16_w32x32_2cta_mbar");
       rc = launch_modes<CfgM>(cplx, amode, bmode, q, s, a2, b2, e2);
     } else {

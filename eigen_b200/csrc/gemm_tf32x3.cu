@@ -1250,7 +1250,7 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
     prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + CP_BN - 1) / CP_BN;
     prm.kchunk = kchunk_blocks();
     prm.uplo = p.uplo; prm.herm = p.herm;
-    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES));
+    B200_SET_MAX_DYN_SMEM_ONCE(tf32x3_cgemm_pair_kernel, CP_SMEM_BYTES);
     int64_t pairs = sm_count() / 2;
     if (ptiles < pairs) pairs = ptiles;
     note_variant("tf32x3_tcgen05_c_pair_256x128x32");
@@ -1271,7 +1271,7 @@ static int launch_tf32x3_cplx(const GemmProblem& p, cudaStream_t s, float* ws) {
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + CTN - 1) / CTN;
   prm.kchunk = kchunk_blocks();
     prm.uplo = p.uplo; prm.herm = p.herm;
-  B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_cgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CSMEM_BYTES));   // per device and cheap: set on every launch
+  B200_SET_MAX_DYN_SMEM_ONCE(tf32x3_cgemm_kernel, CSMEM_BYTES);
   const int64_t ntiles = prm.tiles_m * prm.tiles_n;
   const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());
   note_variant("tf32x3_tcgen05_c_128x64x32");
@@ -1319,7 +1319,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     prm.tiles_m = (p.m + TM2 - 1) / TM2; prm.tiles_n = (p.n + TN - 1) / TN;
     prm.kchunk = 1 << 30;
     prm.uplo = 0;
-    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+    B200_SET_MAX_DYN_SMEM_ONCE(tf32x3_gemm256_kernel, SMEM2_BYTES);
     const int64_t nt = prm.tiles_m * prm.tiles_n;
     const unsigned g2 = (unsigned)(nt < sm_count() ? nt : sm_count());
     note_variant("tf32x3_tcgen05_256x256x16");
@@ -1346,7 +1346,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
     prm.tiles_m = (p.m + 255) / 256; prm.tiles_n = (p.n + 255) / 256;
     prm.kchunk = kchunk_blocks();
     prm.uplo = p.uplo;
-    B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
+    B200_SET_MAX_DYN_SMEM_ONCE(tf32x3_gemm_pair_kernel, P_SMEM_BYTES);
     const int64_t nt = prm.tiles_m * prm.tiles_n;
     int64_t pairs = sm_count() / 2;
     if (nt < pairs) pairs = nt;
@@ -1367,7 +1367,7 @@ int launch_tf32x3(const GemmProblem& p, cudaStream_t s, void* workspace, size_t 
   prm.tiles_m = (p.m + TM - 1) / TM; prm.tiles_n = (p.n + TN - 1) / TN;
   prm.kchunk = kchunk_blocks();
     prm.uplo = p.uplo;
-  B200_CUDA_TRY(cudaFuncSetAttribute(tf32x3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));   // per device and cheap: set on every launch
+  B200_SET_MAX_DYN_SMEM_ONCE(tf32x3_gemm_kernel, SMEM_BYTES);
   const int64_t ntiles = prm.tiles_m * prm.tiles_n;
   const unsigned grid = (unsigned)(ntiles < sm_count() ? ntiles : sm_count());  // persistent: one CTA per SM
   note_variant("tf32x3_tcgen05_128x256x32");

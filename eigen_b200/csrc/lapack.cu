@@ -50,42 +50,67 @@ template <typename T> __device__ __forceinline__ T sc_div(T a, T b) {
 }
 
 // ---- Cholesky leaf -------------------------------------------------------------------------------------------------------
-// Right-looking Cholesky of a d x d diagonal block (d <= NB) by one warp.  S[i][j], i >= j, is the lower-canonical
-// element: A(i,j) for uplo = L, conj(A(j,i)) for uplo = U (the reference factors the transpose for Upper, LLT.h:367-380).
+// Right-looking Cholesky of a d x d diagonal block (d <= NB) by one warp: lane i keeps row i of the lower-canonical
+// block in registers (a[j] = element (i, j), j <= i; element (i, j) = A(i,j) for uplo = L, conj(A(j,i)) for uplo = U --
+// the reference factors the transpose for Upper, LLT.h:367-380), columns travel between lanes by shuffles.
 // A non-positive pivot at column k stores d0 + k + 1 into *info (smallest wins) and stops, like LLT.h:316-317.
+template <typename T> __device__ __forceinline__ T sc_shfl(T v, int src) {
+  if constexpr (sizeof(T) == sizeof(typename Sc<T>::real)) return __shfl_sync(0xffffffffu, v, src);
+  else { T r; r.x = __shfl_sync(0xffffffffu, v.x, src); r.y = __shfl_sync(0xffffffffu, v.y, src); return r; }
+}
+
+// sqrt(x) and 1/sqrt(x) for the pivot.  The IEEE double sqrt and divide are multi-hundred-cycle software sequences on
+// the critical path of every column; a float rsqrt seed refined by two Newton steps in double (relative error ~1e-16,
+// then one correction of the root) costs a few dependent FMAs.  Out-of-float-range pivots take the IEEE path.
+__device__ __forceinline__ void pivot_roots(double x, double& root, double& inv_root) {
+  if (x > 1e-30 && x < 1e30) {
+    double r = (double)rsqrtf((float)x);
+    r = r * fma(-0.5 * x, r * r, 1.5);
+    r = r * fma(-0.5 * x, r * r, 1.5);
+    double l = x * r;
+    l = fma(0.5 * r, fma(-l, l, x), l);
+    root = l; inv_root = r;
+  } else {
+    root = sqrt(x); inv_root = 1.0 / root;
+  }
+}
+__device__ __forceinline__ void pivot_roots(float x, float& root, float& inv_root) { root = sqrtf(x); inv_root = 1.0f / root; }
+
 template <typename T, int NB>
 __global__ void __launch_bounds__(32) potf2_leaf_kernel(int upper, int d, int64_t d0, T* __restrict__ A, int64_t lda, int* __restrict__ info) {
   using R = typename Sc<T>::real;
-  __shared__ T S[NB][NB + 1];
   const int lane = threadIdx.x;
-  {
-    T v[NB];   // the lane's whole row in flight at once
+  T a[NB];   // the lane's whole row in flight at once
 #pragma unroll
-    for (int j = 0; j < NB; ++j)
-      v[j] = (j < d && lane < d && lane >= j) ? (upper ? A[j + (int64_t)lane * lda] : A[lane + (int64_t)j * lda]) : Sc<T>::zero();
-#pragma unroll
-    for (int j = 0; j < NB; ++j)
-      if (j < d && lane < d && lane >= j) S[lane][j] = upper ? Sc<T>::conj(v[j]) : v[j];
+  for (int j = 0; j < NB; ++j) {
+    a[j] = (j < d && lane < d && lane >= j) ? (upper ? A[j + (int64_t)lane * lda] : A[lane + (int64_t)j * lda]) : Sc<T>::zero();
+    if (upper) a[j] = Sc<T>::conj(a[j]);
   }
-  __syncwarp();
-  for (int k = 0; k < d; ++k) {
-    const R x = sc_real<T>(S[k][k]);
-    if (x <= (R)0) {   // warp-uniform; a NaN pivot continues, as in the reference
-      if (lane == 0) atomicMin(info, (int)(d0 + k + 1));
-      break;
+  bool ok = true;   // warp-uniform
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    if (k < d && ok) {
+      const R x = sc_real<T>(sc_shfl<T>(a[k], k));
+      if (x <= (R)0) {   // a NaN pivot continues, as in the reference
+        if (lane == 0) atomicMin(info, (int)(d0 + k + 1));
+        ok = false;
+      } else {
+        R l, rl;
+        pivot_roots(x, l, rl);
+        if (lane == k) a[k] = sc_from_real<T>(l);
+        else if (lane > k) a[k] = sc_scale<T>(a[k], rl);
+#pragma unroll
+        for (int j = k + 1; j < NB; ++j) {
+          const T ljk = sc_shfl<T>(a[k], j);   // L(j, k), final
+          if (lane >= j) sc_fnma<T>(a[j], a[k], Sc<T>::conj(ljk));
+        }
+      }
     }
-    const R l = sqrt(x);
-    __syncwarp();
-    if (lane == k) S[k][k] = sc_from_real<T>(l);
-    if (lane > k && lane < d) S[lane][k] = sc_div_real<T>(S[lane][k], l);
-    __syncwarp();
-    for (int j = k + 1; j < d; ++j)
-      if (lane >= j && lane < d) sc_fnma<T>(S[lane][j], S[lane][k], Sc<T>::conj(S[j][k]));
-    __syncwarp();
   }
-  for (int j = 0; j < d; ++j)
-    if (lane < d && lane >= j) {
-      if (upper) A[j + (int64_t)lane * lda] = Sc<T>::conj(S[lane][j]); else A[lane + (int64_t)j * lda] = S[lane][j];
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+    if (j < d && lane < d && lane >= j) {
+      if (upper) A[j + (int64_t)lane * lda] = Sc<T>::conj(a[j]); else A[lane + (int64_t)j * lda] = a[j];
     }
 }
 
@@ -393,7 +418,7 @@ int launch_panel(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t 
   int rows_per_cta = (int)((mrows + G - 1) / G);
   const size_t smem = (size_t)rows_per_cta * (NBP + 1) * sizeof(T);
   if (smem + 4096 > cx.max_dyn_smem) return (int)cudaErrorInvalidConfiguration;   // panel taller than ~120k rows
-  B200_CUDA_TRY(cudaFuncSetAttribute(getf2_panel_kernel<T, NBP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B200_SET_MAX_DYN_SMEM_ONCE((getf2_panel_kernel<T, NBP>), cx.max_dyn_smem - 4096);   // the largest slab any panel may need
   B200_CUDA_TRY(cudaMemsetAsync(cx.panel_scratch, 0, 64, s));
   T* A = (T*)p.A + j0 + j0 * p.lda;
   int nb = (int)nc;
@@ -445,7 +470,7 @@ int getrf_typed(const GetrfProblem& p, cudaStream_t s) {
   int optin = 0;
   B200_CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   cx.max_dyn_smem = (size_t)optin;
-  B200_CUDA_TRY(cudaFuncSetAttribute(perm_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024));
+  B200_SET_MAX_DYN_SMEM_ONCE(perm_build_kernel, optin - 1024);
   const int64_t size = std::min(p.m, p.n);
   // workspace: permutation lists (4 * size ints + m ints for the slow path), panel scratch, gather buffer
   const size_t ints = (size_t)size * 3 + 16 + (size_t)p.m;

@@ -19,45 +19,53 @@ namespace b200 {
 namespace {
 
 // ---- leaf: S x = b (SOLVE) or x := S b (multiply) for every right-hand-side vector ---------------------------------------------
-// S is the NB x NB canonical matrix that multiplies a right-hand-side VECTOR from the left:
+// S is the canonical matrix of order <= LB = NSUB * NB that multiplies a right-hand-side VECTOR from the left:
 //   side = left :  S = op(A) block,      vectors = columns of B
 //   side = right:  S = op(A)^T block,    vectors = rows of B          (X op(A) = B  <=>  op(A)^T X^T = B^T)
 // Entries outside the referenced triangle are zero, a unit diagonal is one, and rows/columns past nb are the identity,
-// so the fully unrolled NB-step recurrence is valid for every nb <= NB.  In SOLVE mode the diagonal holds reciprocals
+// so the unrolled NB-step recurrences are valid for every nb <= LB.  In SOLVE mode the diagonal holds reciprocals
 // (the reference multiplies by 1/diag as well, TriangularSolverMatrix.h:118-121).
+// One thread owns one right-hand-side vector and walks it in NSUB sub-vectors of NB elements held in registers:
+// the contributions of the other sub-vectors (re-read from B: own earlier stores in a solve, still-original values in a
+// product) are NB x NB register-blocked rank updates against the shared-memory block, then the NB x NB diagonal block is
+// solved / applied by a fully unrolled recurrence.  One launch therefore replaces 2*NSUB-1 launches of the recursion.
 constexpr int LEAF_THREADS = 256;   // one right-hand-side vector per thread
 
-template <typename T, int NB, bool LOWER, bool SOLVE>
+template <typename T, int NB, int NSUB, bool LOWER, bool SOLVE>
 __global__ void __launch_bounds__(LEAF_THREADS)
 tri_leaf_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrhs, const T* __restrict__ A, int64_t lda,
-                T* __restrict__ B, int64_t ldb) {
-  __shared__ T S[NB][NB];
+                T* B, int64_t ldb) {
+  constexpr int LB = NB * NSUB;
+  extern __shared__ __align__(16) unsigned char leaf_smem[];
+  T* S = reinterpret_cast<T*>(leaf_smem);   // S[i * LB + j]; every access is a warp-wide broadcast
   {
-    // all loads of the block are issued before any is consumed (a load-per-iteration loop costs one DRAM latency each)
-    constexpr int PER = (NB * NB + LEAF_THREADS - 1) / LEAF_THREADS;
-    T vals[PER];
+    // all loads of a batch are issued before any is consumed (a load-per-iteration loop costs one DRAM latency each);
+    // p runs along the stored column of A so that the global reads are coalesced
     const bool swap = left ? (op != OP_N) : (op == OP_N);
+    constexpr int BATCH = (LB * LB / LEAF_THREADS >= 16) ? 16 : 8;
+    for (int base = 0; base < LB * LB; base += LEAF_THREADS * BATCH) {
+      T vals[BATCH];
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-      const int idx = threadIdx.x + q * LEAF_THREADS;
-      const int i = idx % NB, j = idx / NB;
-      const int r = swap ? j : i, c = swap ? i : j;   // element of A
-      const bool referenced = idx < NB * NB && i < nb && j < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
-      vals[q] = referenced ? A[r + c * lda] : ((i == j) ? sc_one<T>() : Sc<T>::zero());
-    }
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-      const int idx = threadIdx.x + q * LEAF_THREADS;
-      if (idx >= NB * NB) continue;
-      const int i = idx % NB, j = idx / NB;
-      const int r = swap ? j : i, c = swap ? i : j;
-      const bool referenced = i < nb && j < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
-      T v = vals[q];
-      if (referenced) {
-        if (op == OP_C) v = Sc<T>::conj(v);
-        if (SOLVE && r == c) v = sc_recip<T>(v);
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * LEAF_THREADS + threadIdx.x;
+        const int r = idx % LB, c = idx / LB;   // element of A
+        const bool referenced = idx < LB * LB && r < nb && c < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
+        vals[q] = referenced ? A[r + c * lda] : ((r == c) ? sc_one<T>() : Sc<T>::zero());
       }
-      S[i][j] = v;
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * LEAF_THREADS + threadIdx.x;
+        if (idx >= LB * LB) continue;
+        const int r = idx % LB, c = idx / LB;
+        const bool referenced = r < nb && c < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
+        T v = vals[q];
+        if (referenced) {
+          if (op == OP_C) v = Sc<T>::conj(v);
+          if (SOLVE && r == c) v = sc_recip<T>(v);
+        }
+        const int i = swap ? c : r, j = swap ? r : c;   // position in S
+        S[i * LB + j] = v;
+      }
     }
   }
   __syncthreads();
@@ -65,47 +73,93 @@ tri_leaf_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrhs, cons
   if (v >= nrhs) return;
   T* bp = left ? B + v * ldb : B + v;
   const int64_t bs = left ? 1 : ldb;
-  T x[NB];
+  const int nsub = (nb + NB - 1) / NB;
+  // sub-vector order: a lower solve / upper product goes top-down, an upper solve / lower product bottom-up
+  constexpr bool ASCENDING = (SOLVE == LOWER);
+  for (int step = 0; step < nsub; ++step) {
+    const int b = ASCENDING ? step : nsub - 1 - step;
+    const T* Sb = S + (b * NB) * LB;   // rows of sub-block b
+    T x[NB];
 #pragma unroll
-  for (int i = 0; i < NB; ++i) x[i] = (i < nb) ? bp[i * bs] : Sc<T>::zero();
-  if constexpr (SOLVE) {
-    if constexpr (LOWER) {
+    for (int i = 0; i < NB; ++i) x[i] = (b * NB + i < nb) ? bp[(int64_t)(b * NB + i) * bs] : Sc<T>::zero();
+    if constexpr (!SOLVE) {
+      // diagonal block first (in place; the off-diagonal terms below only add)
+      const T* D = Sb + b * NB;
+      if constexpr (LOWER) {
 #pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        x[j] = Sc<T>::mul(x[j], S[j][j]);
+        for (int i = NB - 1; i >= 0; --i) {
+          T acc = Sc<T>::mul(D[i * LB + i], x[i]);
 #pragma unroll
-        for (int i = j + 1; i < NB; ++i) sc_fnma<T>(x[i], S[i][j], x[j]);
-      }
-    } else {
+          for (int j = 0; j < i; ++j) Sc<T>::fma(acc, D[i * LB + j], x[j]);
+          x[i] = acc;
+        }
+      } else {
 #pragma unroll
-      for (int j = NB - 1; j >= 0; --j) {
-        x[j] = Sc<T>::mul(x[j], S[j][j]);
+        for (int i = 0; i < NB; ++i) {
+          T acc = Sc<T>::mul(D[i * LB + i], x[i]);
 #pragma unroll
-        for (int i = 0; i < j; ++i) sc_fnma<T>(x[i], S[i][j], x[j]);
-      }
-    }
-  } else {
-    if constexpr (LOWER) {   // x_i := sum_{j <= i} S_ij x_j, bottom-up so the inputs are still intact
-#pragma unroll
-      for (int i = NB - 1; i >= 0; --i) {
-        T acc = Sc<T>::mul(S[i][i], x[i]);
-#pragma unroll
-        for (int j = 0; j < i; ++j) Sc<T>::fma(acc, S[i][j], x[j]);
-        x[i] = acc;
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < NB; ++i) {
-        T acc = Sc<T>::mul(S[i][i], x[i]);
-#pragma unroll
-        for (int j = i + 1; j < NB; ++j) Sc<T>::fma(acc, S[i][j], x[j]);
-        x[i] = acc;
+          for (int j = i + 1; j < NB; ++j) Sc<T>::fma(acc, D[i * LB + j], x[j]);
+          x[i] = acc;
+        }
       }
     }
+    // the other sub-vectors this one depends on: c < b for a lower S, c > b for an upper S.  Their elements come from
+    // global memory in chunks of 8; the next chunk is requested before the current one is consumed, so one load
+    // latency is exposed per sub-vector pair instead of one per chunk.
+    {
+      const int c_lo = LOWER ? 0 : b + 1, c_hi = LOWER ? b : nsub;
+      constexpr int CH = 8;
+      T cur[CH], nxt[CH];
+      int c = c_lo, j0 = 0;
+      bool have = c < c_hi;
+      if (have) {
+#pragma unroll
+        for (int q = 0; q < CH; ++q) cur[q] = (c * NB + j0 + q < nb) ? bp[(int64_t)(c * NB + j0 + q) * bs] : Sc<T>::zero();
+      }
+      while (have) {
+        int c2 = c, j2 = j0 + CH;
+        if (j2 == NB) { j2 = 0; ++c2; }
+        const bool have2 = c2 < c_hi;
+        if (have2) {
+#pragma unroll
+          for (int q = 0; q < CH; ++q) nxt[q] = (c2 * NB + j2 + q < nb) ? bp[(int64_t)(c2 * NB + j2 + q) * bs] : Sc<T>::zero();
+        }
+        const T* Sc_ = Sb + c * NB + j0;
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+#pragma unroll
+          for (int i = 0; i < NB; ++i) {
+            if constexpr (SOLVE) sc_fnma<T>(x[i], Sc_[i * LB + q], cur[q]);
+            else Sc<T>::fma(x[i], Sc_[i * LB + q], cur[q]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < CH; ++q) cur[q] = nxt[q];
+        c = c2; j0 = j2; have = have2;
+      }
+    }
+    if constexpr (SOLVE) {
+      const T* D = Sb + b * NB;
+      if constexpr (LOWER) {
+#pragma unroll
+        for (int j = 0; j < NB; ++j) {
+          x[j] = Sc<T>::mul(x[j], D[j * LB + j]);
+#pragma unroll
+          for (int i = j + 1; i < NB; ++i) sc_fnma<T>(x[i], D[i * LB + j], x[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = NB - 1; j >= 0; --j) {
+          x[j] = Sc<T>::mul(x[j], D[j * LB + j]);
+#pragma unroll
+          for (int i = 0; i < j; ++i) sc_fnma<T>(x[i], D[i * LB + j], x[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i)
+      if (b * NB + i < nb) bp[(int64_t)(b * NB + i) * bs] = x[i];
   }
-#pragma unroll
-  for (int i = 0; i < NB; ++i)
-    if (i < nb) bp[i * bs] = x[i];
 }
 
 // ---- B := alpha * B (alpha == 0: B := 0 without reading it) over an m x n window -----------------------------------------------
@@ -153,8 +207,9 @@ __global__ void __launch_bounds__(256) symm_expand_kernel(int uplo, int herm, in
   }
 }
 
-template <typename T> struct LeafOrder { static constexpr int NB = 32; };
-template <> struct LeafOrder<double2> { static constexpr int NB = 16; };
+// sub-vector length held in registers, and sub-vectors per leaf: leaves have order <= NB * NSUB (128; 64 for complex double)
+template <typename T> struct LeafOrder { static constexpr int NB = 32; static constexpr int NSUB = 4; };
+template <> struct LeafOrder<double2> { static constexpr int NB = 16; static constexpr int NSUB = 4; };
 
 template <typename T>
 T scalar_of(const double a[2]) {
@@ -164,15 +219,19 @@ T scalar_of(const double a[2]) {
 
 template <typename T, bool SOLVE>
 int launch_leaf(const TriProblem& p, bool s_lower, int64_t d0, int nb, cudaStream_t s) {
-  constexpr int NB = LeafOrder<T>::NB;
+  constexpr int NB = LeafOrder<T>::NB, NSUB = LeafOrder<T>::NSUB, LB = NB * NSUB;
   const T* A = (const T*)p.A + d0 + d0 * p.lda;
   T* B = p.left ? (T*)p.B + d0 : (T*)p.B + d0 * p.ldb;
   const int64_t nrhs = p.left ? p.n : p.m;
   const unsigned grid = (unsigned)((nrhs + LEAF_THREADS - 1) / LEAF_THREADS);
-  if (s_lower)
-    tri_leaf_kernel<T, NB, true, SOLVE><<<grid, LEAF_THREADS, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
-  else
-    tri_leaf_kernel<T, NB, false, SOLVE><<<grid, LEAF_THREADS, 0, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+  constexpr size_t smem = (size_t)LB * LB * sizeof(T);
+  if (s_lower) {
+    B200_SET_MAX_DYN_SMEM_ONCE((tri_leaf_kernel<T, NB, NSUB, true, SOLVE>), smem);
+    tri_leaf_kernel<T, NB, NSUB, true, SOLVE><<<grid, LEAF_THREADS, smem, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+  } else {
+    B200_SET_MAX_DYN_SMEM_ONCE((tri_leaf_kernel<T, NB, NSUB, false, SOLVE>), smem);
+    tri_leaf_kernel<T, NB, NSUB, false, SOLVE><<<grid, LEAF_THREADS, smem, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+  }
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -212,10 +271,10 @@ static int64_t split_point(int64_t d, int nb) {   // largest nb * 2^j strictly b
 // Triangle rows/columns [d0, d0 + d).  t_lower: op(A) is lower triangular.
 template <typename T, bool SOLVE>
 int tri_recurse(const TriProblem& p, bool t_lower, int64_t d0, int64_t d, cudaStream_t s) {
-  constexpr int NB = LeafOrder<T>::NB;
+  constexpr int LB = LeafOrder<T>::NB * LeafOrder<T>::NSUB;
   const bool s_lower = p.left ? t_lower : !t_lower;   // S = T (left) or T^T (right)
-  if (d <= NB) return launch_leaf<T, SOLVE>(p, s_lower, d0, (int)d, s);
-  const int64_t d1 = split_point(d, NB), d2 = d - d1;
+  if (d <= LB) return launch_leaf<T, SOLVE>(p, s_lower, d0, (int)d, s);
+  const int64_t d1 = split_point(d, LB), d2 = d - d1;
   // which diagonal block goes first: in a solve, the one whose unknowns feed the other; in a product (in place), the
   // one whose inputs are not needed by the other any more
   // solve, left:  T lower -> (1) first; T upper -> (2) first.   solve, right: X T = B: T lower -> (2) first; upper -> (1).
