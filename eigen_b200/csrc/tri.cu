@@ -7,8 +7,8 @@
 // The reference blocks the triangle into small panels solved by substitution and pushes everything else through
 // gebp_kernel.  Here the same split is recursive: a triangle of order d is cut at d1 (a power-of-two multiple of the
 // leaf order), the off-diagonal block becomes ONE large product on the tensor-pipe GEMM kernels (gemm_dmma.cu /
-// gemm_tf32x3.cu) and only leaves of order <= NB are handled by a register-resident substitution kernel, one
-// right-hand-side vector per thread.  Symmetric / Hermitian operands are expanded from the referenced triangle into a
+// gemm_tf32x3.cu) and only leaves of order <= 128 (64 for complex double) are handled by a substitution kernel, one
+// right-hand-side vector per thread, walked in register-resident sub-vectors of 32 elements.  Symmetric / Hermitian operands are expanded from the referenced triangle into a
 // dense device image (what blas/level3_impl.h:324-341 does on the host for the complex case) and multiplied by the
 // GEMM kernels.
 #include "../../include/b200blas.h"
