@@ -455,15 +455,178 @@ def run_ours(args):
     return 0
 
 
+# ---- widened rows: ?syrk_ ?trsm_ ?trmm_ ?symm_ ?syr2k_ ?potrf_ ?getrf_ ------------------------------
+# Same line shape as the headline workloads; one F77 call per step.  These are diagnostic workloads (single GPU): the
+# driver's default run never selects them.  Measured lines live in profiles/bench_r01/level3_*.jsonl.
+LEVEL3_ROUTINES = ("syrk", "trsm", "trmm", "symm", "syr2k", "potrf", "getrf")
+LEVEL3_WORKLOADS = {"%s%s%d" % (t, r, n): (t, r, n) for t in "sd" for r in LEVEL3_ROUTINES for n in (2048, 8192, 16384)}
+
+
+def level3_flops(r, n):
+    return {"syrk": n ** 3 * 1.0, "trsm": n ** 3 * 1.0, "trmm": n ** 3 * 1.0, "symm": 2.0 * n ** 3, "syr2k": 2.0 * n ** 3,
+            "potrf": n ** 3 / 3.0, "getrf": 2.0 * n ** 3 / 3.0}[r]
+
+
+def level3_call(lib, t, r, n, pa, pb, pc, ipiv):
+    """The F77 call of one step (side / uplo / trans = L / L / N, alpha = 1 (syrk: -1), beta = 0 (syrk: 1))."""
+    rt = C.c_float if t == "s" else C.c_double
+    one, zero, mone = rt(1.0), rt(0.0), rt(-1.0)
+    nn = C.c_int(n)
+    info = C.c_int(0)
+    bn = C.byref(nn)
+    f = getattr(lib, t + r + "_")
+    if r == "syrk":
+        return lambda: f(b"L", b"N", bn, bn, C.byref(mone), pa, bn, C.byref(one), pc, bn)
+    if r in ("trsm", "trmm"):
+        return lambda: f(b"L", b"L", b"N", b"N", bn, bn, C.byref(one), pa, bn, pb, bn)
+    if r in ("symm", "syr2k"):
+        c1, c2 = (b"L", b"L") if r == "symm" else (b"L", b"N")
+        return lambda: f(c1, c2, bn, bn, C.byref(one), pa, bn, pb, bn, C.byref(zero), pc, bn)
+    if r == "potrf":
+        return lambda: f(b"L", bn, pa, bn, C.byref(info))
+    return lambda: f(bn, bn, pa, bn, ipiv.ctypes.data_as(C.POINTER(C.c_int)), C.byref(info))
+
+
+def level3_cpu_reference(t, r, cn):
+    """The reference's own routine (oracle/_ref; its blas/ and lapack/ are single-threaded) at a bounded order cn."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as oa
+    npdt = np.float32 if t == "s" else np.float64
+    rng = np.random.default_rng(7)
+    m = rng.uniform(-1, 1, (cn, cn))
+    if r == "potrf":
+        a = np.asfortranarray((m @ m.T / cn + np.eye(cn)).astype(npdt))
+    elif r in ("trsm", "trmm"):
+        a = np.asfortranarray((m * (2.0 / cn) + 1.5 * np.eye(cn)).astype(npdt))
+    else:
+        a = np.asfortranarray(m.astype(npdt))
+    b = np.asfortranarray(rng.uniform(-1, 1, (cn, cn)).astype(npdt))
+    c = np.ones((cn, cn), dtype=npdt, order="F")
+    cpiv = np.zeros(cn, dtype=np.int32)
+    lib = oa.ref_lapack() if r in ("potrf", "getrf") else oa.ref_blas()
+    call = level3_call(lib, t, r, cn, oa._ptr(a), oa._ptr(b), oa._ptr(c), cpiv)
+    t0 = time.perf_counter()
+    call()
+    dt_s = time.perf_counter() - t0
+    return {"value": level3_flops(r, cn) / dt_s / 1e12, "unit": "TFLOP/s", "cores": 1, "kind": "reference",
+            "sample": "%s%s_ of oracle/_ref (the reference's blas/ and lapack/ are single-threaded) at n=%d" % (t, r, cn)}, dt_s * 1e3
+
+
+def run_level3(args):
+    t, r, n = LEVEL3_WORKLOADS[args.workload]
+    metric = "%s%s TFLOP/s at n=%d" % (t, r, n)
+    config = {"workload": "%s: %s%s_ order %d, side/uplo/trans = L/L/N, uniform[-1,1] operands (potrf: M M^T / n + I; trsm/trmm: "
+                          "unit-scale triangle), column-major, ld = n" % (args.workload, t, r, n),
+              "l2": "operands larger than L2 for n >= 8192; no explicit flush", "parallelism": "1 GPU"}
+    dtype = "f64" if t == "d" else "f32"
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        cpu, ms = level3_cpu_reference(t, r, 2048)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cpu["value"], "unit": "TFLOP/s", "n_gpus": args.gpus,
+                          "steps": 1, "warmup": 0, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config, "cpu_baseline": cpu,
+                          "e2e": {"value": cpu["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return 0
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"metric": metric, "unavailable": "the level-3 / LAPACK workloads are single-GPU (replicas only)"}))
+        return 0
+    import numpy as np
+    import torch
+    import eigen_b200
+    L = eigen_b200.require_device()
+    dt = torch.float32 if t == "s" else torch.float64
+    eigen_b200.pipe_peak(0, 1500)   # ramp the clocks before the denominators are measured
+    pipe = 0 if t == "d" else 3
+    peak = max(eigen_b200.pipe_peak(pipe, 800), eigen_b200.pipe_peak(pipe, 800))
+    g = torch.Generator(device="cuda").manual_seed(7)
+    M = torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    if r == "potrf":
+        src = (M @ M.T / n + torch.eye(n, dtype=torch.float64, device="cuda")).to(dt)
+    elif r in ("trsm", "trmm"):
+        src = (M * (2.0 / n) + torch.eye(n, dtype=torch.float64, device="cuda") * 1.5).to(dt)
+    else:
+        src = M.to(dt)
+    Bd = (torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1).to(dt)
+    Cd = torch.ones(n, n, dtype=dt, device="cuda")
+    del M
+    ipiv = np.zeros(n, dtype=np.int32)
+    inplace_a = r in ("potrf", "getrf")
+    A = src.clone()
+    call = level3_call(L, t, r, n, C.c_void_p(A.data_ptr()), C.c_void_p(Bd.data_ptr()), C.c_void_p(Cd.data_ptr()), ipiv)
+    clocks = ClockSampler(0)
+    clocks.start()
+    times, launches = [], 0
+    for i in range(args.warmup + args.steps):
+        if inplace_a:
+            A.copy_(src)
+        torch.cuda.synchronize()
+        if i == args.warmup:
+            clocks.mark()
+        l0 = eigen_b200.kernel_launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= args.warmup:
+            times.append(e0.elapsed_time(e1))
+            launches = eigen_b200.kernel_launches() - l0
+    clk = clocks.stop()
+    ms = sum(times) / len(times)
+    fl = level3_flops(r, n)
+    variant = eigen_b200.last_variant()
+    # e2e: the same F77 call on pinned HOST operands
+    hA, hB, hC = src.cpu().pin_memory(), Bd.cpu().pin_memory(), Cd.cpu().pin_memory()
+    del A, Bd, Cd, src
+    torch.cuda.empty_cache()
+    hA0 = hA.clone() if inplace_a else None
+    hcall = level3_call(L, t, r, n, C.c_void_p(hA.data_ptr()), C.c_void_p(hB.data_ptr()), C.c_void_p(hC.data_ptr()), ipiv)
+    hcall()
+    e2e = []
+    for _ in range(2):
+        if inplace_a:
+            hA.copy_(hA0)
+        t0 = time.perf_counter()
+        hcall()
+        e2e.append((time.perf_counter() - t0) * 1e3)
+    h2d, d2h = C.c_uint64(), C.c_uint64()
+    L.b200blas_last_transfer(C.byref(h2d), C.byref(d2h))
+    del hA, hB, hC, hA0
+    try:
+        cpu, _ = level3_cpu_reference(t, r, 2048)
+    except Exception as e:  # reported, never required
+        cpu = {"value": None, "unit": "TFLOP/s", "cores": 1, "kind": "reference", "sample": "failed: %r" % (e,)}
+    issued = fl * (3.0 if t == "s" else 1.0)
+    print(json.dumps({
+        "metric": metric, "value": fl / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": dtype + ("" if t == "d" else " (3xTF32 products, fp32 leaves)"), "data": "synthetic", "config": config,
+        "gpu_launches": launches * args.steps, "kernel": variant, "clocks": clk,
+        "e2e": {"value": fl / (min(e2e) * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": min(e2e), "h2d_bytes_per_step": h2d.value,
+                "d2h_bytes_per_step": d2h.value, "api": "%s%s_ (F77 C ABI) on pinned host operands" % (t, r)},
+        "roofline": {"bound": "tensor", "achieved": issued / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": issued / (ms * 1e-3) / 1e12 / peak if peak > 0 else None, "traffic": None, "kernel": variant,
+                     "launches_per_step": launches, "algorithmic_flops_per_step": fl,
+                     "note": "composite routine: the products run on the dgemm / sgemm kernels, the rest is the leaf chain (DESIGN.md 3b)"},
+        "cpu_baseline": cpu}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="dgemm16384", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="dgemm16384", choices=sorted(WORKLOADS) + sorted(LEVEL3_WORKLOADS))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.workload in LEVEL3_WORKLOADS:
+        return run_level3(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
