@@ -89,3 +89,18 @@ def test_error_exits_port_and_reference(t):
         lp.run_potrf_error_exits(P, fn, t)
     for label, fn in _fns(t + "getrf_"):
         lp.run_getrf_error_exits(P, fn, t)
+
+
+@pytest.mark.parametrize("t", list("sdcz"))
+def test_pivot_ties_take_the_first_row_port_and_reference(t):
+    """maxCoeff keeps the first largest entry (PartialPivLU.h:378-380); an all-zero first column reports info = 1."""
+    rng = np.random.default_rng(12)
+    for label, fn in _fns(t + "getrf_"):
+        for m, n in ((70, 40), (300, 33)):
+            a = oa.rand_matrix(rng, t, m, n)
+            a[:, 0] = np.where(np.arange(m) % 2 == 0, 1.0, -1.0)
+            ipiv, info = oa.call_getrf(fn, m, n, a.copy(order="F"), m)
+            assert info == 0 and ipiv[0] == 1, (label, t, m, n)
+            a[:, 0] = 0
+            ipiv, info = oa.call_getrf(fn, m, n, a.copy(order="F"), m)
+            assert info == 1 and ipiv[0] == 1, (label, t, m, n)
