@@ -84,3 +84,20 @@ def test_lapack_fuzz(seed):
         pp, ip_ = oa.call_getrf(getattr(P, "oracle_%sgetrf_" % t), m, n, ap, ap.shape[0])
         pr, ir = oa.call_getrf(getattr(R, t + "getrf_"), m, n, ar, ar.shape[0])
         assert ip_ == ir and np.array_equal(pp, pr) and _close(t, ap, ar, 16 * max(n, 1)), (t, "getrf", m, n)
+
+
+def test_reference_getrf_leaves_wide_matrices_unfinished_and_the_port_reproduces_it():
+    """for m < n (min(m, n) > 16) the reference's blocked_lu never updates the columns right of the
+    square part (PartialPivLU.h:457-492 uses tsize = size - k - bs), so its output does not satisfy P A = L U.  The
+    oracle port restates that behaviour bit for pivot; the GPU library deliberately completes the factorization (LAPACK
+    semantics) and parity with the reference is claimed for m >= n only."""
+    rng = np.random.default_rng(5)
+    R = oa.ref_lapack()
+    for (m, n) in [(20, 37), (33, 70)]:
+        a0 = oa.rand_matrix(rng, "d", m, n)
+        ap, ar = a0.copy(order="F"), a0.copy(order="F")
+        pp, ip_ = oa.call_getrf(P.oracle_dgetrf_, m, n, ap, m)
+        pr, ir = oa.call_getrf(R.dgetrf_, m, n, ar, m)
+        assert ip_ == ir and np.array_equal(pp, pr) and _close("d", ap, ar, 16 * m)
+        with pytest.raises(AssertionError):
+            lp.check_getrf("d", m, n, a0, ar, pr, ir)
