@@ -12,6 +12,9 @@ bench/bench_gemm.cpp:130-133,211-214), 2*m*n*k flops per step.
   `cpu_baseline` = the reference's OpenMP gebp path (oracle/_ref) on this box's host cores on a bounded slab.
 * ours, N > 1 (torchrun, one rank per GPU): the product is partitioned by 2-D tiles of C (eigen_b200.parallelize),
   panels broadcast over NCCL, C tiles gathered to rank 0; strong scaling (total work fixed).
+* --workload <t><routine><n> with routine in syrk/trsm/trmm/symm/syr2k/potrf/getrf (SURVEY 8 f rows, single GPU,
+  diagnostic -- never the driver's default): one F77 call per step on device pointers (`value`) and on pinned host
+  operands (`e2e`); `cpu_baseline` / `--impl reference` time the reference's own blas/ or lapack/ routine (oracle/_ref).
 * --impl reference: the reference's own CPU implementation of the path (oracle/_ref/libeigen_gebp_omp.so, Eigen's
   expression API + OpenMP gebp) on the host cores, each step a bounded column slab of the workload.
 """
