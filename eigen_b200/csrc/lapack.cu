@@ -16,6 +16,7 @@
 // Row interchanges outside the panel (xLASWP) are turned into a permutation first (sequential simulation in shared
 // memory) and applied as parallel gathers, instead of a chain of dependent row swaps.
 #include <climits>
+#include <cstdlib>
 
 #include "../../include/b200blas.h"
 #include "common.cuh"
@@ -114,6 +115,54 @@ __global__ void __launch_bounds__(32) potf2_leaf_kernel(int upper, int d, int64_
     }
 }
 
+// ---- DRAFT (round 2, not yet run on hardware; opt-in with B200BLAS_POTF2=cta) --------------------------------------------
+// CTA-wide Cholesky leaf of order d <= NBL: the block lives in shared memory, every column costs two __syncthreads and
+// its trailing update is spread over all 256 threads (the one-warp leaf issues ~8k dependent instructions per 32 x 32
+// block = 34 us; profiles/launches_r01_dpotrf8192_v2.md).
+template <typename T, int NBL>
+__global__ void __launch_bounds__(256) potf2_cta_kernel(int upper, int d, int64_t d0, T* __restrict__ A, int64_t lda, int* __restrict__ info) {
+  using R = typename Sc<T>::real;
+  __shared__ T S[NBL][NBL + 1];   // lower-canonical block, S[i][j] for i >= j
+  __shared__ int failed;
+  const int tid = threadIdx.x;
+  if (tid == 0) failed = 0;
+  for (int idx = tid; idx < NBL * NBL; idx += 256) {
+    const int i = idx % NBL, j = idx / NBL;
+    if (i < d && j <= i) {
+      const T v = upper ? Sc<T>::conj(A[j + (int64_t)i * lda]) : A[i + (int64_t)j * lda];
+      S[i][j] = v;
+    }
+  }
+  __syncthreads();
+  const int ti = tid % NBL, tg = tid / NBL;          // row owned in the trailing update, column group
+  constexpr int GROUPS = 256 / NBL;
+  for (int k = 0; k < d; ++k) {
+    const R x = sc_real<T>(S[k][k]);
+    if (x <= (R)0) {   // uniform: every thread reads the same value
+      if (tid == 0) { atomicMin(info, (int)(d0 + k + 1)); failed = 1; }
+      break;
+    }
+    R l, rl;
+    pivot_roots(x, l, rl);
+    __syncthreads();                                  // everybody has read S[k][k]
+    if (tid == k) S[k][k] = sc_from_real<T>(l);
+    else if (tid > k && tid < d) S[tid][k] = sc_scale<T>(S[tid][k], rl);
+    __syncthreads();                                  // column k is final
+    if (ti < d) {
+      const T lik = S[ti][k];
+      for (int j = k + 1 + tg; j <= ti; j += GROUPS) sc_fnma<T>(S[ti][j], lik, Sc<T>::conj(S[j][k]));
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NBL * NBL; idx += 256) {
+    const int i = idx % NBL, j = idx / NBL;
+    if (i < d && j <= i) {
+      if (upper) A[j + (int64_t)i * lda] = Sc<T>::conj(S[i][j]); else A[i + (int64_t)j * lda] = S[i][j];
+    }
+  }
+}
+
 static int64_t split_point(int64_t d, int nb) {
   int64_t h = nb;
   while (h * 2 < d) h *= 2;
@@ -126,12 +175,19 @@ int potrf_rec(const PotrfProblem& p, int64_t d0, int64_t d, cudaStream_t s) {
   const bool upper = p.uplo == UPLO_UPPER;
   const bool cplx = sizeof(T) != sizeof(typename Sc<T>::real);
   T* A = (T*)p.A;
+  static const bool cta_leaf = [] { const char* e = getenv("B200BLAS_POTF2"); return e && e[0] == 'c'; }();   // DRAFT, opt-in
+  constexpr int NBL = 64 / (sizeof(T) == 16 ? 2 : 1);   // 64 x 65 elements of <= 8 bytes, 32 x 33 of 16 bytes
+  if (cta_leaf && d <= NBL) {
+    potf2_cta_kernel<T, NBL><<<1, 256, 0, s>>>(upper ? 1 : 0, (int)d, d0, A + d0 + d0 * p.lda, p.lda, p.dinfo);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   if (d <= NB) {
     potf2_leaf_kernel<T, NB><<<1, 32, 0, s>>>(upper ? 1 : 0, (int)d, d0, A + d0 + d0 * p.lda, p.lda, p.dinfo);
     count_launch();
     return (int)cudaGetLastError();
   }
-  const int64_t d1 = split_point(d, NB), d2 = d - d1;
+  const int64_t d1 = split_point(d, cta_leaf ? NBL : NB), d2 = d - d1;
   B200_CUDA_TRY(potrf_rec<T>(p, d0, d1, s));
   TriProblem t;
   t.type = p.type; t.uplo = p.uplo; t.op = OP_C; t.unit = 0; t.alpha[0] = 1.0; t.alpha[1] = 0.0;
