@@ -45,6 +45,9 @@ struct TriProblem {
   double alpha[2];
   const void* A; int64_t lda;
   void* B; int64_t ldb;
+  // DRAFT (round 2): inverses of the diagonal leaf blocks (leaf order x leaf order each, ld = leaf order) and a
+  // scratch panel for the out-of-place leaf products; null = substitution leaves
+  const void* Vinv = nullptr; void* Xtmp = nullptr;
 };
 // C := alpha * A * B + beta * C (left) or alpha * B * A + beta * C (right); A symmetric (herm = 0) or Hermitian (herm = 1),
 // only its `uplo` triangle is referenced (?symm_/?hemm_, blas/level3_impl.h:287-355,505-562).  Device pointers.

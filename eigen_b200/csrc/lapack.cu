@@ -16,6 +16,8 @@
 // Row interchanges outside the panel (xLASWP) are turned into a permutation first (sequential simulation in shared
 // memory) and applied as parallel gathers, instead of a chain of dependent row swaps.
 #include <climits>
+#include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "../../include/b200blas.h"
 #include "common.cuh"
@@ -114,6 +116,54 @@ __global__ void __launch_bounds__(32) potf2_leaf_kernel(int upper, int d, int64_
     }
 }
 
+// ---- DRAFT (round 2, not yet run on hardware; opt-in with B200BLAS_POTF2=cta) --------------------------------------------
+// CTA-wide Cholesky leaf of order d <= NBL: the block lives in shared memory, every column costs two __syncthreads and
+// its trailing update is spread over all 256 threads (the one-warp leaf issues ~8k dependent instructions per 32 x 32
+// block = 34 us; profiles/launches_r01_dpotrf8192_v2.md).
+template <typename T, int NBL>
+__global__ void __launch_bounds__(256) potf2_cta_kernel(int upper, int d, int64_t d0, T* __restrict__ A, int64_t lda, int* __restrict__ info) {
+  using R = typename Sc<T>::real;
+  __shared__ T S[NBL][NBL + 1];   // lower-canonical block, S[i][j] for i >= j
+  __shared__ int failed;
+  const int tid = threadIdx.x;
+  if (tid == 0) failed = 0;
+  for (int idx = tid; idx < NBL * NBL; idx += 256) {
+    const int i = idx % NBL, j = idx / NBL;
+    if (i < d && j <= i) {
+      const T v = upper ? Sc<T>::conj(A[j + (int64_t)i * lda]) : A[i + (int64_t)j * lda];
+      S[i][j] = v;
+    }
+  }
+  __syncthreads();
+  const int ti = tid % NBL, tg = tid / NBL;          // row owned in the trailing update, column group
+  constexpr int GROUPS = 256 / NBL;
+  for (int k = 0; k < d; ++k) {
+    const R x = sc_real<T>(S[k][k]);
+    if (x <= (R)0) {   // uniform: every thread reads the same value
+      if (tid == 0) { atomicMin(info, (int)(d0 + k + 1)); failed = 1; }
+      break;
+    }
+    R l, rl;
+    pivot_roots(x, l, rl);
+    __syncthreads();                                  // everybody has read S[k][k]
+    if (tid == k) S[k][k] = sc_from_real<T>(l);
+    else if (tid > k && tid < d) S[tid][k] = sc_scale<T>(S[tid][k], rl);
+    __syncthreads();                                  // column k is final
+    if (ti < d) {
+      const T lik = S[ti][k];
+      for (int j = k + 1 + tg; j <= ti; j += GROUPS) sc_fnma<T>(S[ti][j], lik, Sc<T>::conj(S[j][k]));
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int idx = tid; idx < NBL * NBL; idx += 256) {
+    const int i = idx % NBL, j = idx / NBL;
+    if (i < d && j <= i) {
+      if (upper) A[j + (int64_t)i * lda] = Sc<T>::conj(S[i][j]); else A[i + (int64_t)j * lda] = S[i][j];
+    }
+  }
+}
+
 static int64_t split_point(int64_t d, int nb) {
   int64_t h = nb;
   while (h * 2 < d) h *= 2;
@@ -126,12 +176,19 @@ int potrf_rec(const PotrfProblem& p, int64_t d0, int64_t d, cudaStream_t s) {
   const bool upper = p.uplo == UPLO_UPPER;
   const bool cplx = sizeof(T) != sizeof(typename Sc<T>::real);
   T* A = (T*)p.A;
+  static const bool cta_leaf = [] { const char* e = getenv("B200BLAS_POTF2"); return e && e[0] == 'c'; }();   // DRAFT, opt-in
+  constexpr int NBL = 64 / (sizeof(T) == 16 ? 2 : 1);   // 64 x 65 elements of <= 8 bytes, 32 x 33 of 16 bytes
+  if (cta_leaf && d <= NBL) {
+    potf2_cta_kernel<T, NBL><<<1, 256, 0, s>>>(upper ? 1 : 0, (int)d, d0, A + d0 + d0 * p.lda, p.lda, p.dinfo);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   if (d <= NB) {
     potf2_leaf_kernel<T, NB><<<1, 32, 0, s>>>(upper ? 1 : 0, (int)d, d0, A + d0 + d0 * p.lda, p.lda, p.dinfo);
     count_launch();
     return (int)cudaGetLastError();
   }
-  const int64_t d1 = split_point(d, NB), d2 = d - d1;
+  const int64_t d1 = split_point(d, cta_leaf ? NBL : NB), d2 = d - d1;
   B200_CUDA_TRY(potrf_rec<T>(p, d0, d1, s));
   TriProblem t;
   t.type = p.type; t.uplo = p.uplo; t.op = OP_C; t.unit = 0; t.alpha[0] = 1.0; t.alpha[1] = 0.0;
@@ -300,6 +357,133 @@ getf2_panel_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, i
     for (int r = tid; r < R; r += 256) A[(r0 + r) + (int64_t)c * lda] = slab[r * LDS + c];
 }
 
+// ---- DRAFT (round 2, compiled but not yet run on hardware; opt-in with B200BLAS_GETF2=cluster) ---------------------------
+// The same panel factorization on ONE thread-block cluster: the slab of every CTA lives in its shared memory, the
+// per-column exchange goes through distributed shared memory and the barrier is the hardware cluster barrier instead
+// of a global-atomic grid barrier (4.1 us per column in round 1, profiles/launches_r01_dgetrf8192_v2.md).
+// Per column: local arg-max -> each CTA writes its candidate (score, row, row contents; the owner of row k also row k)
+// into slot [my rank] of EVERY CTA's candidate table (remote stores) -> cluster.sync() -> identical local reduction ->
+// swap / scale / update.  Tables are double-buffered by column parity, so one barrier per column suffices.
+namespace cg = cooperative_groups;
+
+template <typename T, int NBP, int MAXCL>
+struct ClusterTables {
+  double score[2][MAXCL];
+  int row[2][MAXCL];
+  T vals[2][MAXCL][NBP];
+  T rowk[2][NBP];
+};
+
+template <typename T, int NBP, int MAXCL>
+__global__ void __launch_bounds__(256)
+getf2_cluster_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, int64_t lda, int* __restrict__ ipiv, int64_t row_base,
+                     int* __restrict__ info, int64_t col_base) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* slab = reinterpret_cast<T*>(smem_raw);   // slab[r * (NBP + 1) + c]
+  constexpr int LDS = NBP + 1;
+  __shared__ ClusterTables<T, NBP, MAXCL> tab;
+  __shared__ T prow[NBP], krow[NBP];
+  __shared__ double red_score[8];
+  __shared__ int red_row[8];
+  __shared__ double win_score;
+  __shared__ int win_row;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cta = (int)cluster.block_rank(), tid = threadIdx.x;
+  const int64_t r0 = (int64_t)cta * rows_per_cta;
+  const int R = (int)max((int64_t)0, min((int64_t)rows_per_cta, mrows - r0));
+  for (int r = tid; r < R; r += 256)
+    for (int c0 = 0; c0 < nb; c0 += 8) {
+      T v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = (c0 + q < nb) ? A[(r0 + r) + (int64_t)(c0 + q) * lda] : Sc<T>::zero();
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (c0 + q < nb) slab[r * LDS + c0 + q] = v[q];
+    }
+  cluster.sync();   // every CTA's shared memory is live before anybody writes into it remotely
+  const int steps = (int)min((int64_t)nb, mrows);
+  for (int k = 0; k < steps; ++k) {
+    const int par = k & 1;
+    double best = -1.0;
+    int brow = INT_MAX;
+    for (int r = tid; r < R; r += 256) {
+      const int64_t gr = r0 + r;
+      if (gr < k) continue;
+      const double sc = sc_score<T>(slab[r * LDS + k]);
+      if (sc > best || (sc == best && (int)gr < brow)) { best = sc; brow = (int)gr; }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+      if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+    }
+    if ((tid & 31) == 0) { red_score[tid >> 5] = best; red_row[tid >> 5] = brow; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (red_score[w] > best || (red_score[w] == best && red_row[w] < brow)) { best = red_score[w]; brow = red_row[w]; }
+      win_score = best; win_row = brow;
+    }
+    __syncthreads();
+    {
+      // publish into every CTA's table (thread t handles peer t % CL, value index t / CL ... simple strided loops)
+      const double ls = win_score;
+      const int lr = win_row;
+      const bool own_k = (k >= r0 && k < r0 + R);
+      for (int peer = 0; peer < CL; ++peer) {
+        ClusterTables<T, NBP, MAXCL>* rt = cluster.map_shared_rank(&tab, peer);
+        if (tid == 0) { rt->score[par][cta] = ls; rt->row[par][cta] = lr; }
+        if (ls >= 0.0 && tid < nb) rt->vals[par][cta][tid] = slab[(lr - (int)r0) * LDS + tid];
+        if (own_k && tid >= 32 && tid < 32 + nb) rt->rowk[par][tid - 32] = slab[(k - (int)r0) * LDS + tid - 32];
+      }
+    }
+    cluster.sync();   // release / acquire at cluster scope: the remote stores are visible
+    if (tid < 32) {
+      double gb = -1.0;
+      int grow = INT_MAX, gw = -1;
+      for (int w = tid; w < CL; w += 32) {
+        const double s2 = tab.score[par][w];
+        const int r2 = tab.row[par][w];
+        if (s2 >= 0.0 && (s2 > gb || (s2 == gb && r2 < grow))) { gb = s2; grow = r2; gw = w; }
+      }
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, gb, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, grow, off);
+        const int ow = __shfl_xor_sync(0xffffffffu, gw, off);
+        if (ob > gb || (ob == gb && orow < grow)) { gb = ob; grow = orow; gw = ow; }
+      }
+      if (gw < 0) { gb = 0.0; grow = k; }
+      if (tid == 0) { win_score = gb; win_row = grow; }
+      if (tid < nb && gw >= 0) { prow[tid] = tab.vals[par][gw][tid]; krow[tid] = tab.rowk[par][tid]; }
+    }
+    __syncthreads();
+    const double gscore = win_score;
+    const int piv = win_row;
+    if (cta == 0 && tid == 0) {
+      ipiv[k] = (int)(row_base + piv + 1);
+      if (gscore == 0.0) atomicMin(info, (int)(col_base + k + 1));
+    }
+    if (gscore != 0.0) {
+      if (piv != k) {
+        if (k >= r0 && k < r0 + R && tid < nb) slab[(k - (int)r0) * LDS + tid] = prow[tid];
+        if (piv >= r0 && piv < r0 + R && tid < nb) slab[(piv - (int)r0) * LDS + tid] = krow[tid];
+      }
+      __syncthreads();
+      const T pv = prow[k];
+      for (int r = tid; r < R; r += 256) {
+        if (r0 + r <= k) continue;
+        T* row = slab + r * LDS;
+        const T l = sc_div<T>(row[k], pv);
+        row[k] = l;
+        for (int j = k + 1; j < nb; ++j) sc_fnma<T>(row[j], l, prow[j]);
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = 0; c < nb; ++c)
+    for (int r = tid; r < R; r += 256) A[(r0 + r) + (int64_t)c * lda] = slab[r * LDS + c];
+  cluster.sync();   // nobody exits while a peer may still write into its tables
+}
+
 // ---- row interchanges as a permutation -----------------------------------------------------------------------------------
 // Simulate ipiv[k0 .. k0+ns) (1-based global rows, relative base row_base = k0) on an index array held in shared memory.
 // Output: src_top[k] = source row of destination row k (k < ns), and the list of displaced destinations r >= ns with
@@ -413,6 +597,28 @@ template <typename T>
 int launch_panel(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t nc, cudaStream_t s) {
   constexpr int NBP = Leaf<T>::NB;
   const int64_t mrows = p.m - j0;
+  static const bool use_cluster = [] { const char* e = getenv("B200BLAS_GETF2"); return e && e[0] == 'c'; }();   // DRAFT, opt-in
+  if (use_cluster) {
+    constexpr int MAXCL = 16;
+    int cl = (int)std::min<int64_t>(MAXCL, (mrows + 255) / 256);
+    if (cl < 1) cl = 1;
+    int rpc = (int)((mrows + cl - 1) / cl);
+    const size_t smem_c = (size_t)rpc * (NBP + 1) * sizeof(T);
+    if (smem_c + sizeof(ClusterTables<T, NBP, MAXCL>) + 4096 <= cx.max_dyn_smem) {
+      auto kern = getf2_cluster_kernel<T, NBP, MAXCL>;
+      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cl); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem_c; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mrows, (int)nc, rpc, (T*)p.A + j0 + j0 * p.lda, p.lda, p.dipiv + j0, j0, p.dinfo, j0));
+      count_launch();
+      return 0;
+    }   // taller than 16 CTAs' shared memory: the cooperative-grid kernel below
+  }
   int G = (int)std::min<int64_t>(cx.sms, (mrows + 255) / 256);   // about one panel row per thread; G <= 256 (candidate reduce)
   if (G < 1) G = 1;
   int rows_per_cta = (int)((mrows + G - 1) / G);

@@ -11,6 +11,8 @@
 // right-hand-side vector per thread, walked in register-resident sub-vectors of 32 elements.  Symmetric / Hermitian operands are expanded from the referenced triangle into a
 // dense device image (what blas/level3_impl.h:324-341 does on the host for the complex case) and multiplied by the
 // GEMM kernels.
+#include <cstdlib>
+
 #include "../../include/b200blas.h"
 #include "common.cuh"
 #include "scalar.cuh"
@@ -162,6 +164,83 @@ tri_leaf_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrhs, cons
   }
 }
 
+// ---- DRAFT (round 2, compiled but not yet run on hardware; opt-in with B200BLAS_TRSM=inv) --------------------------------
+// Inverses of all diagonal leaf blocks of T = op(A) in ONE launch (one CTA per block), so that a leaf of the solve is a
+// product X_b = inv(T_bb) * B_b on the tensor-pipe kernels instead of 8256 FMA + LDS per right-hand side on the SIMT
+// pipe (profiles/launches_r01_dpotrf8192_v2.md).  The block is brought to lower-canonical form Lc (T itself, or T^T
+// for an upper T), split into halves [L11 0; L21 L22]; threads 0..2H-1 invert L11 and L22 one column each (registers,
+// broadcast reads of the block), then all threads form X21 = -X22 * (L21 * X11); V = X (or X^T for an upper T).
+template <typename T, int IB>
+__global__ void __launch_bounds__(256)
+trtri_diag_kernel(int op, int uplo, int unit, int t_lower, int64_t n, const T* __restrict__ A, int64_t lda, T* __restrict__ V) {
+  constexpr int H = IB / 2;
+  extern __shared__ __align__(16) unsigned char inv_smem[];
+  T* L11 = reinterpret_cast<T*>(inv_smem);   // [i * H + j]
+  T* L22 = L11 + H * H;
+  T* L21 = L22 + H * H;
+  T* X11 = L21 + H * H;
+  T* X22 = X11 + H * H;
+  const int tid = threadIdx.x;
+  const int64_t d0 = (int64_t)blockIdx.x * IB;
+  const int nb = (int)min((int64_t)IB, n - d0);
+  const T* Ab = A + d0 + d0 * lda;
+  T* Vb = V + (int64_t)blockIdx.x * IB * IB;
+  for (int idx = tid; idx < IB * IB; idx += 256) {
+    const int i = idx % IB, j = idx / IB;   // element (i, j) of Lc
+    T v = (i == j) ? sc_one<T>() : Sc<T>::zero();
+    if (i >= j && i < nb && j < nb) {
+      const int ti = t_lower ? i : j, tj = t_lower ? j : i;            // element of T
+      const int r = (op == OP_N) ? ti : tj, c = (op == OP_N) ? tj : ti;   // element of A
+      const bool referenced = (r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c);
+      if (referenced) { v = Ab[r + c * lda]; if (op == OP_C) v = Sc<T>::conj(v); }
+      else if (r != c) v = Sc<T>::zero();
+    }
+    if (i < H && j < H) L11[i * H + j] = (i >= j) ? v : Sc<T>::zero();
+    else if (i >= H && j >= H) L22[(i - H) * H + (j - H)] = (i >= j) ? v : Sc<T>::zero();
+    else if (i >= H && j < H) L21[(i - H) * H + j] = v;
+  }
+  __syncthreads();
+  if (tid < 2 * H) {
+    const T* L = tid < H ? L11 : L22;
+    T* X = tid < H ? X11 : X22;
+    const int j = tid % H;
+    T x[H];
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+      T acc = (i == j) ? sc_one<T>() : Sc<T>::zero();
+#pragma unroll
+      for (int q = 0; q < i; ++q) sc_fnma<T>(acc, L[i * H + q], x[q]);   // x[q] = 0 for q < j: uniform control flow
+      x[i] = (i < j) ? Sc<T>::zero() : Sc<T>::mul(acc, sc_recip<T>(L[i * H + i]));
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) X[i * H + j] = x[i];
+  }
+  __syncthreads();
+  T* M = L11;   // L11 is dead: M = L21 * X11
+  for (int idx = tid; idx < H * H; idx += 256) {
+    const int i = idx / H, j = idx % H;
+    T acc = Sc<T>::zero();
+    for (int q = j; q < H; ++q) Sc<T>::fma(acc, L21[i * H + q], X11[q * H + j]);   // X11 is lower: rows q >= j
+    M[i * H + j] = acc;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < IB * IB; idx += 256) {
+    const int i = idx % IB, j = idx / IB;   // element (i, j) of X = inv(Lc)
+    T v = Sc<T>::zero();
+    if (i >= j) {
+      if (i < H) v = X11[i * H + j];
+      else if (j >= H) v = X22[(i - H) * H + (j - H)];
+      else {
+        T acc = Sc<T>::zero();
+        for (int q = 0; q <= i - H; ++q) sc_fnma<T>(acc, X22[(i - H) * H + q], M[q * H + j]);   // X22 lower: columns q <= i - H
+        v = acc;
+      }
+    }
+    if (t_lower) Vb[i + j * IB] = v; else Vb[j + i * IB] = v;   // V = X or X^T; the other triangle gets its zeros from (j, i)
+    if (i > j) { if (t_lower) Vb[j + i * IB] = Sc<T>::zero(); else Vb[i + j * IB] = Sc<T>::zero(); }
+  }
+}
+
 // ---- B := alpha * B (alpha == 0: B := 0 without reading it) over an m x n window -----------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) window_scale_kernel(int64_t m, int64_t n, T alpha, bool zero, T* __restrict__ B, int64_t ldb) {
@@ -223,6 +302,17 @@ int launch_leaf(const TriProblem& p, bool s_lower, int64_t d0, int nb, cudaStrea
   const T* A = (const T*)p.A + d0 + d0 * p.lda;
   T* B = p.left ? (T*)p.B + d0 : (T*)p.B + d0 * p.ldb;
   const int64_t nrhs = p.left ? p.n : p.m;
+  if (SOLVE && p.Vinv) {   // DRAFT: X_b = inv(T_bb) * B_b (or B_b * inv(T_bb)) out of place, then copied back
+    const T* Vb = (const T*)p.Vinv + (d0 / LB) * (int64_t)LB * LB;
+    GemmProblem g;
+    g.type = p.type; g.opa = OP_N; g.opb = OP_N; g.k = nb;
+    g.alpha[0] = 1.0; g.alpha[1] = 0.0; g.beta[0] = 0.0; g.beta[1] = 0.0;
+    if (p.left) { g.m = nb; g.n = nrhs; g.A = Vb; g.lda = LB; g.B = B; g.ldb = p.ldb; g.C = p.Xtmp; g.ldc = LB; }
+    else { g.m = nrhs; g.n = nb; g.A = B; g.lda = p.ldb; g.B = Vb; g.ldb = LB; g.C = p.Xtmp; g.ldc = nrhs; }
+    B200_CUDA_TRY(run_gemm_device(g, s, B200BLAS_AUTO));
+    return (int)cudaMemcpy2DAsync(B, (size_t)p.ldb * sizeof(T), p.Xtmp, (size_t)g.ldc * sizeof(T), (size_t)g.m * sizeof(T), (size_t)g.n,
+                                  cudaMemcpyDeviceToDevice, s);
+  }
   const unsigned grid = (unsigned)((nrhs + LEAF_THREADS - 1) / LEAF_THREADS);
   constexpr size_t smem = (size_t)LB * LB * sizeof(T);
   if (s_lower) {
@@ -309,7 +399,27 @@ int run_tri(const TriProblem& p, cudaStream_t s) {
   const bool zero = p.alpha[0] == 0.0 && p.alpha[1] == 0.0;
   if (!zero) {   // alpha == 0: the result is zero whatever A holds (netlib ?TRSM/?TRMM quick path)
     const bool t_lower = (p.uplo == UPLO_LOWER) == (p.op == OP_N);
-    B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, 0, p.left ? p.m : p.n, s)));
+    static const bool use_inv = [] { const char* e = getenv("B200BLAS_TRSM"); return e && e[0] == 'i'; }();   // DRAFT, opt-in
+    if (SOLVE && use_inv) {
+      constexpr int LB = LeafOrder<T>::NB * LeafOrder<T>::NSUB;
+      const int64_t na = p.left ? p.m : p.n, nrhs = p.left ? p.n : p.m;
+      const int64_t nblocks = (na + LB - 1) / LB;
+      const size_t vbytes = (size_t)nblocks * LB * LB * sizeof(T), xbytes = (size_t)LB * (size_t)nrhs * sizeof(T);
+      unsigned char* ws = nullptr;
+      B200_CUDA_TRY(cudaMallocAsync((void**)&ws, vbytes + xbytes + 256, s));
+      constexpr size_t smem = 5 * (size_t)(LB / 2) * (LB / 2) * sizeof(T);
+      B200_SET_MAX_DYN_SMEM_ONCE((trtri_diag_kernel<T, LB>), smem);
+      trtri_diag_kernel<T, LB><<<(unsigned)nblocks, 256, smem, s>>>(p.op, p.uplo, p.unit, t_lower ? 1 : 0, na, (const T*)p.A, p.lda, (T*)ws);
+      count_launch();
+      int e = (int)cudaGetLastError();
+      TriProblem q = p;
+      q.Vinv = ws; q.Xtmp = ws + (vbytes + 255) / 256 * 256;
+      if (!e) e = tri_recurse<T, SOLVE>(q, t_lower, 0, na, s);
+      cudaFreeAsync(ws, s);
+      if (e) return e;
+    } else {
+      B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, 0, p.left ? p.m : p.n, s)));
+    }
   }
   // the reference scales after the solve / inside the product (blas/level3_impl.h:174-175, :278-281)
   return scale_window<T>(p.m, p.n, p.alpha, (T*)p.B, p.ldb, s);
