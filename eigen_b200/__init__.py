@@ -24,7 +24,32 @@ EXPORTS = ["sgemm_", "dgemm_", "cgemm_", "zgemm_", "ssyrk_", "dsyrk_", "csyrk_",
            "chemm_", "zhemm_", "ssyr2k_", "dsyr2k_", "csyr2k_", "zsyr2k_", "cher2k_", "zher2k_",
            "spotrf_", "dpotrf_", "cpotrf_", "zpotrf_", "sgetrf_", "dgetrf_", "cgetrf_", "zgetrf_", "xerbla_", "b200blas_gemm_dev", "b200blas_version",
            "b200blas_device_ok", "b200blas_last_error", "b200blas_last_variant", "b200blas_kernel_launches",
-           "b200blas_set_variant", "b200blas_last_transfer", "b200blas_release", "b200blas_pipe_peak"]
+           "b200blas_set_variant", "b200blas_last_transfer", "b200blas_release", "b200blas_pipe_peak",
+           "b200blas_set_devices", "b200blas_get_devices", "b200blas_set_grid", "b200blas_host_register",
+           "b200blas_host_unregister", "b200blas_multi_plan"]
+
+
+class Region(C.Structure):
+    """b200blas_region (include/b200blas.h section 3)"""
+    _fields_ = [("loc", C.c_int), ("buf", C.c_int), ("r0", C.c_int64), ("c0", C.c_int64), ("rows", C.c_int64), ("cols", C.c_int64)]
+
+
+class Step(C.Structure):
+    """b200blas_step"""
+    _fields_ = [("kind", C.c_int), ("dev", C.c_int), ("stream", C.c_int), ("x", Region), ("y", Region), ("z", Region),
+                ("opa", C.c_int), ("opb", C.c_int), ("alpha", C.c_double * 2), ("beta", C.c_double * 2),
+                ("nwait", C.c_int), ("wait", C.c_int * 4), ("record", C.c_int)]
+
+
+PLAN_MAXDEV, PLAN_MAXCHUNK = 8, 64
+
+
+class PlanInfo(C.Structure):
+    """b200blas_plan_info"""
+    _fields_ = [("ndev", C.c_int), ("pr", C.c_int), ("pc", C.c_int), ("nchunks", C.c_int), ("ngroups", C.c_int), ("host_origin", C.c_int),
+                ("row_cut", C.c_int64 * (PLAN_MAXDEV + 1)), ("col_cut", C.c_int64 * (PLAN_MAXDEV + 1)), ("k_cut", C.c_int64 * (PLAN_MAXCHUNK + 1)),
+                ("group_first_chunk", C.c_int * (PLAN_MAXCHUNK + 1)), ("ld", (C.c_int64 * 4) * PLAN_MAXDEV), ("elems", (C.c_int64 * 4) * PLAN_MAXDEV),
+                ("nsteps", C.c_int)]
 
 _lib = None
 
@@ -92,6 +117,12 @@ def lib():
     L.b200blas_last_transfer.argtypes = [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     L.b200blas_pipe_peak.argtypes = [i, i]
     L.b200blas_pipe_peak.restype = C.c_double
+    L.b200blas_set_devices.argtypes = [i]
+    L.b200blas_set_grid.argtypes = [i, i]
+    L.b200blas_host_register.argtypes = [vp, C.c_uint64]
+    L.b200blas_host_unregister.argtypes = [vp]
+    L.b200blas_multi_plan.argtypes = [i, C.c_char, C.c_char, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                      C.c_int64, C.c_int64, C.c_int64, i, i, i, i, C.POINTER(PlanInfo), C.POINTER(Step), i]
     _lib = L
     return L
 
@@ -155,3 +186,21 @@ def kernel_launches():
 def pipe_peak(pipe, millis=300):
     """TFLOP/s of a register-resident loop on pipe 0=DMMA fp64, 1=DFMA, 2=FFMA, 3=tcgen05 tf32."""
     return float(require_device().b200blas_pipe_peak(pipe, millis))
+
+
+def set_devices(n):
+    """Use n GPUs of this box for large products behind ?gemm_ / gemm_dev (include/b200blas.h section 3); returns the count in effect."""
+    return int(lib().b200blas_set_devices(int(n)))
+
+
+def multi_plan(t, transa, transb, m, n, k, alpha, beta, ndev, grid=(0, 0), host_origin=False, cap=4096):
+    """The partition plan of one product as data: (PlanInfo, [Step, ...]).  Pure host arithmetic -- works without a GPU."""
+    al = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
+    be = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
+    info = PlanInfo()
+    steps = (Step * cap)()
+    ns = lib().b200blas_multi_plan(TYPE_CODE[t], transa.encode(), transb.encode(), m, n, k, al, be, 0, 0, 0, ndev, grid[0], grid[1],
+                                   1 if host_origin else 0, C.byref(info), steps, cap)
+    if ns < 0 or ns > cap:
+        raise ValueError("b200blas_multi_plan failed (%d)" % ns)
+    return info, [steps[i] for i in range(ns)]

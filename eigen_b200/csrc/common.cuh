@@ -86,6 +86,13 @@ int launch_symm(const SymmProblem& p, cudaStream_t s, void* workspace);
 int launch_potrf(const PotrfProblem& p, cudaStream_t s);   // lapack.cu
 int launch_getrf(const GetrfProblem& p, cudaStream_t s);
 
+// multi.cu: the multi-device partitioner behind ?gemm_ / b200blas_gemm_dev.  multi_wanted: N > 1 devices are enabled and
+// the product is large enough; multi_gemm returns a cudaError_t as int.  host_origin: operands are host pointers
+// (the call is synchronous); otherwise they live on the current device and the call is asynchronous on `stream`.
+bool multi_wanted(const GemmProblem& p);
+int multi_gemm(const GemmProblem& p, bool host_origin, cudaStream_t stream, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+void multi_release();
+
 void count_launch(int n = 1);
 void note_variant(const char* name);
 

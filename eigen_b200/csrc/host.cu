@@ -9,6 +9,7 @@
 // upload of slab j+1, the product on slab j and the download of slab j-1 overlap (the GPU analogue of the kc/nc
 // panel streaming of GeneralMatrixMatrix.h:155-198).  There is no CPU fallback.
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <condition_variable>
 #include <cstdlib>
@@ -20,6 +21,7 @@
 
 #include "../../include/b200blas.h"
 #include "common.cuh"
+#include "staging.cuh"
 
 namespace b200 {
 
@@ -40,6 +42,20 @@ static int fail(int cuda_err) {
     cudaGetLastError();  // clear sticky-less errors
   }
   return cuda_err;
+}
+
+// B200BLAS_LOG=1: one line per F77 product call on stderr (shape, operand residency, kernel variant, wall ms)
+static bool log_enabled() {
+  static const bool v = [] { const char* e = getenv("B200BLAS_LOG"); return e && e[0] && e[0] != '0'; }();
+  return v;
+}
+static double wall_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static void log_call(const char* name, char ta, char tb, int64_t m, int64_t n, int64_t k, const char* where, double ms, int err) {
+  fprintf(stderr, "[b200blas] %.6s %c%c m=%lld n=%lld k=%lld operands=%s devices=%d variant=%s %.3f ms h2d=%llu d2h=%llu%s\n", name, ta, tb,
+          (long long)m, (long long)n, (long long)k, where, b200blas_get_devices(), t_variant, ms, (unsigned long long)t_h2d,
+          (unsigned long long)t_d2h, err ? " FAILED" : "");
 }
 
 static int op_of(char x) {
@@ -134,285 +150,14 @@ static void load_scalar(int type, const void* p, double out[2]) {
   }
 }
 
-// ---- pageable operands: pinned staging ring + copy workers -------------------------------------------------------
-// Eigen matrices are ordinary pageable memory.  A cudaMemcpy2DAsync from pageable memory is staged by the driver in
-// small synchronous pieces (~11 GB/s measured through bench_gemm -DHAVE_BLAS).  Instead, worker threads copy the
-// operand into a ring of pinned buffers (several threads are needed to outrun one PCIe Gen5 x16 link) and each filled
-// buffer goes to the device with one asynchronous 2-D DMA while the workers fill the next one.
-class CopyPool {
- public:
-  explicit CopyPool(int nthreads) : stop_(false), gen_(0), pending_(0) {
-    for (int i = 0; i < nthreads; ++i) th_.emplace_back([this] { worker(); });
-  }
-  ~CopyPool() {
-    { std::lock_guard<std::mutex> l(mu_); stop_ = true; ++gen_; }
-    cv_.notify_all();
-    for (auto& t : th_) t.join();
-  }
-  // dst/src 2-D regions of `ncols` columns of `width` bytes with the given pitches; returns when the copy is done
-  void copy2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t ncols) {
-    if (width * ncols < (1u << 20) || th_.empty()) {
-      for (size_t j = 0; j < ncols; ++j) memcpy(dst + j * dpitch, src + j * spitch, width);
-      return;
-    }
-    std::unique_lock<std::mutex> call(call_mu_);  // one parallel copy at a time
-    {
-      std::lock_guard<std::mutex> l(mu_);
-      job_ = {dst, dpitch, src, spitch, width, ncols};
-      // split every column into pieces of <= 1 MiB so that tall-and-thin regions parallelise as well
-      piece_ = width > (1u << 20) ? (1u << 20) : width;
-      pieces_per_col_ = (width + piece_ - 1) / piece_;
-      next_.store(0);
-      total_ = ncols * pieces_per_col_;
-      pending_ = (int)th_.size();
-      ++gen_;
-    }
-    cv_.notify_all();
-    run();  // the caller works too
-    std::unique_lock<std::mutex> l(mu_);
-    done_cv_.wait(l, [this] { return pending_ == 0; });
-  }
 
- private:
-  struct Job { char* dst; size_t dpitch; const char* src; size_t spitch; size_t width; size_t ncols; };
-  void run() {
-    for (;;) {
-      const size_t i = next_.fetch_add(1);
-      if (i >= total_) break;
-      const size_t col = i / pieces_per_col_, off = (i % pieces_per_col_) * piece_;
-      const size_t len = off + piece_ <= job_.width ? piece_ : job_.width - off;
-      memcpy(job_.dst + col * job_.dpitch + off, job_.src + col * job_.spitch + off, len);
-    }
-  }
-  void worker() {
-    uint64_t seen = 0;
-    for (;;) {
-      {
-        std::unique_lock<std::mutex> l(mu_);
-        cv_.wait(l, [&] { return gen_ != seen; });
-        seen = gen_;
-        if (stop_) return;
-      }
-      run();
-      {
-        std::lock_guard<std::mutex> l(mu_);
-        if (--pending_ == 0) done_cv_.notify_all();
-      }
-    }
-  }
-  std::vector<std::thread> th_;
-  std::mutex mu_, call_mu_;
-  std::condition_variable cv_, done_cv_;
-  bool stop_;
-  uint64_t gen_;
-  int pending_;
-  Job job_{};
-  size_t piece_ = 0, pieces_per_col_ = 1, total_ = 0;
-  std::atomic<size_t> next_{0};
-};
-
-static CopyPool& copy_pool() {
-  static CopyPool pool([] {
-    const char* e = getenv("B200BLAS_COPY_THREADS");
-    int n = e ? atoi(e) : 0;
-    if (n <= 0) {
-      const unsigned hc = std::thread::hardware_concurrency();
-      n = hc >= 16 ? 7 : hc >= 8 ? 5 : hc >= 4 ? 3 : 1;
-    }
-    return n - 1 < 0 ? 0 : n - 1;  // the calling thread is the n-th copier
-  }());
-  return pool;
-}
-
-static bool is_pageable(const void* p) {
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
-  return at.type == cudaMemoryTypeUnregistered;
-}
-
-struct PinnedRing;
-static int ring_d2h_triangle(PinnedRing& ring, char* dst, size_t dpitch, const char* src, size_t spitch, size_t n, size_t es,
-                             int uplo, cudaStream_t s);
-struct PinnedRing {
-  static constexpr int NBUF = 4;
-  static constexpr size_t BYTES = (size_t)32 << 20;
-  char* buf[NBUF] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t free_ev[NBUF];
-  bool used[NBUF] = {false, false, false, false};
-  int next = 0;
-  bool ready = false;
-  int init() {
-    if (ready) return 0;
-    for (int i = 0; i < NBUF; ++i) {
-      B200_CUDA_TRY(cudaHostAlloc((void**)&buf[i], BYTES, cudaHostAllocDefault));
-      B200_CUDA_TRY(cudaEventCreateWithFlags(&free_ev[i], cudaEventDisableTiming));
-    }
-    ready = true;
-    return 0;
-  }
-  void release() {
-    if (!ready) return;
-    for (int i = 0; i < NBUF; ++i) { cudaFreeHost(buf[i]); cudaEventDestroy(free_ev[i]); buf[i] = nullptr; used[i] = false; }
-    ready = false;
-  }
-  // host (pageable) -> device, 2-D, through the ring; asynchronous with respect to the device stream
-  int h2d(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t ncols, cudaStream_t s) {
-    if (width == 0 || ncols == 0) return 0;
-    if (width > BYTES) return (int)cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, ncols, cudaMemcpyHostToDevice, s);
-    { const int e = init(); if (e) return e; }
-    const size_t cols_per = BYTES / width;
-    for (size_t c0 = 0; c0 < ncols; c0 += cols_per) {
-      const size_t nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
-      const int slot = next;
-      next = (next + 1) % NBUF;
-      if (used[slot]) B200_CUDA_TRY(cudaEventSynchronize(free_ev[slot]));
-      copy_pool().copy2d(buf[slot], width, src + c0 * spitch, spitch, width, nc);
-      B200_CUDA_TRY(cudaMemcpy2DAsync(dst + c0 * dpitch, dpitch, buf[slot], width, width, nc, cudaMemcpyHostToDevice, s));
-      B200_CUDA_TRY(cudaEventRecord(free_ev[slot], s));
-      used[slot] = true;
-    }
-    return 0;
-  }
-  // device -> host (pageable), 2-D, through the ring; returns when the data is in the caller's memory
-  int d2h(char* dst, size_t dpitch, const char* src, size_t spitch, size_t width, size_t ncols, cudaStream_t s) {
-    if (width == 0 || ncols == 0) return 0;
-    if (width > BYTES) {
-      B200_CUDA_TRY(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, ncols, cudaMemcpyDeviceToHost, s));
-      return (int)cudaStreamSynchronize(s);
-    }
-    { const int e = init(); if (e) return e; }
-    const size_t cols_per = BYTES / width;
-    // software pipeline over the ring: DMA of chunk i+1 runs while the workers copy chunk i out
-    size_t issued = 0, retired = 0;
-    const size_t nchunks = (ncols + cols_per - 1) / cols_per;
-    while (retired < nchunks) {
-      while (issued < nchunks && issued - retired < (size_t)NBUF) {
-        const size_t c0 = issued * cols_per, nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
-        const int slot = (int)(issued % NBUF);
-        B200_CUDA_TRY(cudaMemcpy2DAsync(buf[slot], width, src + c0 * spitch, spitch, width, nc, cudaMemcpyDeviceToHost, s));
-        B200_CUDA_TRY(cudaEventRecord(free_ev[slot], s));
-        used[slot] = false;
-        ++issued;
-      }
-      const size_t c0 = retired * cols_per, nc = ncols - c0 < cols_per ? ncols - c0 : cols_per;
-      const int slot = (int)(retired % NBUF);
-      B200_CUDA_TRY(cudaEventSynchronize(free_ev[slot]));
-      copy_pool().copy2d(dst + c0 * dpitch, dpitch, buf[slot], width, width, nc);
-      ++retired;
-    }
-    return 0;
-  }
-};
-
-// device -> host for a rank-k update: whole columns travel into the pinned ring, but only the referenced triangle of
-// each column is copied into the caller's matrix (the other triangle is not referenced by ?syrk_/?herk_ and may be
-// in use by the caller).  Returns when the data is in place.
-static int ring_d2h_triangle(PinnedRing& ring, char* dst, size_t dpitch, const char* src, size_t spitch, size_t n, size_t es,
-                             int uplo, cudaStream_t s) {
-  if (n == 0) return 0;
-  const size_t width = n * es;
-  { const int e = ring.init(); if (e) return e; }
-  const size_t cols_per = width > PinnedRing::BYTES ? 0 : PinnedRing::BYTES / width;
-  if (cols_per == 0) {
-    // a single column exceeds a ring buffer (n > 4M doubles): copy the triangle column by column
-    for (size_t j = 0; j < n; ++j) {
-      const size_t lo = uplo == UPLO_UPPER ? 0 : j, hi = uplo == UPLO_UPPER ? j + 1 : n;
-      B200_CUDA_TRY(cudaMemcpyAsync(dst + j * dpitch + lo * es, src + j * spitch + lo * es, (hi - lo) * es, cudaMemcpyDeviceToHost, s));
-    }
-    return (int)cudaStreamSynchronize(s);
-  }
-  const size_t nchunks = (n + cols_per - 1) / cols_per;
-  size_t issued = 0, retired = 0;
-  while (retired < nchunks) {
-    while (issued < nchunks && issued - retired < (size_t)PinnedRing::NBUF) {
-      const size_t c0 = issued * cols_per, nc = n - c0 < cols_per ? n - c0 : cols_per;
-      const int slot = (int)(issued % PinnedRing::NBUF);
-      B200_CUDA_TRY(cudaMemcpy2DAsync(ring.buf[slot], width, src + c0 * spitch, spitch, width, nc, cudaMemcpyDeviceToHost, s));
-      B200_CUDA_TRY(cudaEventRecord(ring.free_ev[slot], s));
-      ++issued;
-    }
-    const size_t c0 = retired * cols_per, nc = n - c0 < cols_per ? n - c0 : cols_per;
-    const int slot = (int)(retired % PinnedRing::NBUF);
-    B200_CUDA_TRY(cudaEventSynchronize(ring.free_ev[slot]));
-    for (size_t jj = 0; jj < nc; ++jj) {
-      const size_t j = c0 + jj;
-      const size_t lo = uplo == UPLO_UPPER ? 0 : j, hi = uplo == UPLO_UPPER ? j + 1 : n;
-      memcpy(dst + j * dpitch + lo * es, ring.buf[slot] + jj * width + lo * es, (hi - lo) * es);
-    }
-    ++retired;
-  }
-  return 0;
-}
-
-// ---- per-process staging context ---------------------------------------------------------------------------
-struct Staging {
-  std::mutex mu;
-  int dev = -1;
-  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
-  void* dbuf[3] = {nullptr, nullptr, nullptr};
-  size_t dcap[3] = {0, 0, 0};
-  static constexpr int MAX_SLABS = 64;
-  static constexpr int MAX_ACHUNKS = 8;
-  cudaEvent_t ev_in[MAX_SLABS], ev_comp[MAX_SLABS], ev_ac[MAX_ACHUNKS], ev_a = nullptr;
-  bool ready = false;
-  PinnedRing ring_in, ring_out;   // pageable operands only
-
-  int init() {
-    int d = 0;
-    B200_CUDA_TRY(cudaGetDevice(&d));
-    if (ready && d == dev) return 0;
-    release();
-    dev = d;
-    B200_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-    B200_CUDA_TRY(cudaStreamCreateWithFlags(&s_comp, cudaStreamNonBlocking));
-    B200_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-    B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_a, cudaEventDisableTiming));
-    for (int i = 0; i < MAX_SLABS; ++i) {
-      B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-      B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-    }
-    for (int i = 0; i < MAX_ACHUNKS; ++i) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_ac[i], cudaEventDisableTiming));
-    ready = true;
-    return 0;
-  }
-  int reserve(int i, size_t bytes) {
-    if (bytes <= dcap[i]) return 0;
-    if (dbuf[i]) { cudaFree(dbuf[i]); dbuf[i] = nullptr; dcap[i] = 0; }
-    B200_CUDA_TRY(cudaMalloc(&dbuf[i], bytes));
-    dcap[i] = bytes;
-    return 0;
-  }
-  void release() {
-    if (!ready) return;
-    for (int i = 0; i < 3; ++i) { if (dbuf[i]) cudaFree(dbuf[i]); dbuf[i] = nullptr; dcap[i] = 0; }
-    if (s_in) cudaStreamDestroy(s_in);
-    if (s_comp) cudaStreamDestroy(s_comp);
-    if (s_out) cudaStreamDestroy(s_out);
-    if (ev_a) cudaEventDestroy(ev_a);
-    for (int i = 0; i < MAX_SLABS; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); }
-    for (int i = 0; i < MAX_ACHUNKS; ++i) cudaEventDestroy(ev_ac[i]);
-    ring_in.release();
-    ring_out.release();
-    s_in = s_comp = s_out = nullptr; ev_a = nullptr;
-    ready = false;
-  }
-};
-static Staging g_stage;
-
-static bool is_device_ptr(const void* p) {
-  if (!p) return false;
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-}
-
-static int64_t round_up(int64_t x, int64_t q) { return (x + q - 1) / q * q; }
 
 // Host-operand product: stage, multiply, return.  Returns a cudaError_t (0 = ok).
 static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k, const double alpha[2], const void* a,
                     int64_t lda, const void* b, int64_t ldb, const double beta[2], void* c, int64_t ldc) {
-  std::lock_guard<std::mutex> lock(g_stage.mu);
-  Staging& st = g_stage;
+  StageLease lease;
+  if (!lease.ok()) return (int)cudaErrorInitializationError;
+  Staging& st = lease.st();
   { const int e = st.init(); if (e) return e; }
   const size_t es = (size_t)type_bytes(type);
   const bool beta_zero = (beta[0] == 0.0 && beta[1] == 0.0);
@@ -581,16 +326,23 @@ static int gemm_entry(int type, const char* ta, const char* tb, const int* pm, c
     info = -1;
     return xerbla_(k_names[type], &info, 6);
   }
-  if (dev_c) {
-    GemmProblem p;
-    p.type = type; p.opa = opa; p.opb = opb; p.m = *pm; p.n = *pn; p.k = *pk;
-    p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = beta[0]; p.beta[1] = beta[1];
-    p.A = a; p.lda = *plda; p.B = b; p.ldb = *pldb; p.C = c; p.ldc = *pldc;
+  GemmProblem p;
+  p.type = type; p.opa = opa; p.opb = opb; p.m = *pm; p.n = *pn; p.k = *pk;
+  p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = beta[0]; p.beta[1] = beta[1];
+  p.A = a; p.lda = *plda; p.B = b; p.ldb = *pldb; p.C = c; p.ldc = *pldc;
+  const double t0 = log_enabled() ? wall_ms() : 0.0;
+  if (multi_wanted(p)) {
+    // the parallel split happens INSIDE the product call, as in the reference (Parallelizer.h:85-157): multi.cu
+    t_h2d = t_d2h = 0;
+    err = fail(multi_gemm(p, !dev_c, nullptr, &t_h2d, &t_d2h));
+    if (!err && dev_c) err = fail((int)cudaStreamSynchronize(nullptr));
+  } else if (dev_c) {
     err = run_device(p, nullptr, B200BLAS_AUTO);
     if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
   } else {
     err = fail(run_host(type, opa, opb, *pm, *pn, *pk, alpha, a, *plda, b, *pldb, beta, c, *pldc));
   }
+  if (log_enabled()) log_call(k_names[type], *ta, *tb, *pm, *pn, *pk, dev_c ? "device" : "host", wall_ms() - t0, err);
   if (err) {
     // no CPU fallback by contract: CUDA failures surface through xerbla_ with the reserved info -1
     info = -1;
@@ -607,8 +359,9 @@ static const char* k_syrk_names[4] = {"SSYRK ", "DSYRK ", "CSYRK ", "ZSYRK "};
 static const char* k_herk_names[4] = {"", "", "CHERK ", "ZHERK "};
 
 static int run_host_rankk(const GemmProblem& hp) {
-  std::lock_guard<std::mutex> lock(g_stage.mu);
-  Staging& st = g_stage;
+  StageLease lease;
+  if (!lease.ok()) return (int)cudaErrorInitializationError;
+  Staging& st = lease.st();
   { const int e = st.init(); if (e) return e; }
   const size_t es = (size_t)type_bytes(hp.type);
   const int64_t n = hp.m, k = hp.k;
@@ -683,7 +436,13 @@ static int rankk_entry(int type, bool herk, const char* uplo, const char* op, co
   }
   t_error[0] = 0;
   int err;
-  if (is_device_ptr(c)) {
+  const bool dev_c = is_device_ptr(c);
+  if (product && is_device_ptr(a) != dev_c) {
+    snprintf(t_error, sizeof t_error, "operands must be all host or all device pointers");
+    info = -1;
+    return xerbla_(name, &info, 6);
+  }
+  if (dev_c) {
     err = run_device(p, nullptr, B200BLAS_AUTO);
     if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
   } else {
@@ -777,8 +536,9 @@ static int tri_entry(int type, bool solve, const char* side, const char* uplo, c
     err = fail(solve ? launch_trsm(p, nullptr) : launch_trmm(p, nullptr));
     if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
   } else {
-    std::lock_guard<std::mutex> lock(g_stage.mu);
-    Staging& st = g_stage;
+    StageLease lease;
+    if (!lease.ok()) { info = -1; return xerbla_(name, &info, 6); }
+    Staging& st = lease.st();
     err = st.init();
     const size_t es = (size_t)type_bytes(type);
     const int64_t na = sd ? p.m : p.n;
@@ -846,8 +606,9 @@ static int symm_entry(int type, bool herm, const char* side, const char* uplo, c
     err = alpha_zero ? beta_only(c, *pldc, nullptr) : fail(symm_on_stream(p, nullptr));
     if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
   } else {
-    std::lock_guard<std::mutex> lock(g_stage.mu);
-    Staging& st = g_stage;
+    StageLease lease;
+    if (!lease.ok()) { info = -1; return xerbla_(name, &info, 6); }
+    Staging& st = lease.st();
     err = st.init();
     const size_t es = (size_t)type_bytes(type);
     const int64_t na = sd ? p.m : p.n;
@@ -926,8 +687,9 @@ static int r2k_entry(int type, bool her, const char* uplo, const char* op, const
     err = run(a, *plda, b, *pldb, c, *pldc, nullptr);
     if (!err) err = fail((int)cudaStreamSynchronize(nullptr));
   } else {
-    std::lock_guard<std::mutex> lock(g_stage.mu);
-    Staging& st = g_stage;
+    StageLease lease;
+    if (!lease.ok()) { info = -1; return xerbla_(name, &info, 6); }
+    Staging& st = lease.st();
     err = st.init();
     const size_t es = (size_t)type_bytes(type);
     const int64_t ra = (o == OP_N) ? n : *pk, ca = (o == OP_N) ? *pk : n;
@@ -974,20 +736,18 @@ static int potrf_entry(int type, const char* uplo, const int* pn, void* a, const
   t_error[0] = 0;
   int err = 0, hinfo = INT_MAX;
   const bool dev_a = is_device_ptr(a);
-  std::unique_lock<std::mutex> lock(g_stage.mu, std::defer_lock);
-  Staging& st = g_stage;
+  StageLease lease(false);   // host operands only
   cudaStream_t s = nullptr;
   PotrfProblem p;
   p.type = type; p.uplo = ul; p.n = n; p.A = a; p.lda = *plda;
   int64_t dlda = 0;
   if (!dev_a) {
-    lock.lock();
-    err = st.init();
+    lease.acquire();
+    err = lease.ok() ? lease.st().init() : (int)cudaErrorInitializationError;
     t_h2d = t_d2h = 0;
-    if (!err) err = stage_in(st, 2, a, *plda, n, n, es, true, &dlda);
-    if (!err) err = inputs_ready(st);
-    s = st.s_comp;
-    p.A = st.dbuf[2]; p.lda = dlda;
+    if (!err) err = stage_in(lease.st(), 2, a, *plda, n, n, es, true, &dlda);
+    if (!err) err = inputs_ready(lease.st());
+    if (!err) { s = lease.st().s_comp; p.A = lease.st().dbuf[2]; p.lda = dlda; }
   }
   DevInts di;
   if (!err) err = di.alloc(1, s);
@@ -996,6 +756,7 @@ static int potrf_entry(int type, const char* uplo, const int* pn, void* a, const
   if (!err) err = (int)cudaMemcpyAsync(&hinfo, di.p, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (!err) err = (int)cudaStreamSynchronize(s);
   if (!err && !dev_a) {
+    Staging& st = lease.st();
     err = ring_d2h_triangle(st.ring_out, (char*)a, (size_t)*plda * es, (const char*)st.dbuf[2], (size_t)dlda * es, (size_t)n, es, ul, st.s_out);
     t_d2h += (uint64_t)n * (n + 1) / 2 * es;
   }
@@ -1016,20 +777,18 @@ static int getrf_entry(int type, const int* pm, const int* pn, void* a, const in
   t_error[0] = 0;
   int err = 0, hinfo = INT_MAX;
   const bool dev_a = is_device_ptr(a);
-  std::unique_lock<std::mutex> lock(g_stage.mu, std::defer_lock);
-  Staging& st = g_stage;
+  StageLease lease(false);   // host operands only
   cudaStream_t s = nullptr;
   GetrfProblem p;
   p.type = type; p.m = m; p.n = n; p.A = a; p.lda = *plda;
   int64_t dlda = 0;
   if (!dev_a) {
-    lock.lock();
-    err = st.init();
+    lease.acquire();
+    err = lease.ok() ? lease.st().init() : (int)cudaErrorInitializationError;
     t_h2d = t_d2h = 0;
-    if (!err) err = stage_in(st, 2, a, *plda, m, n, es, true, &dlda);
-    if (!err) err = inputs_ready(st);
-    s = st.s_comp;
-    p.A = st.dbuf[2]; p.lda = dlda;
+    if (!err) err = stage_in(lease.st(), 2, a, *plda, m, n, es, true, &dlda);
+    if (!err) err = inputs_ready(lease.st());
+    if (!err) { s = lease.st().s_comp; p.A = lease.st().dbuf[2]; p.lda = dlda; }
   }
   DevInts di;
   if (!err) err = di.alloc((size_t)size + 1, s);
@@ -1038,7 +797,7 @@ static int getrf_entry(int type, const int* pm, const int* pn, void* a, const in
   if (!err) err = (int)cudaMemcpyAsync(&hinfo, di.p, sizeof(int), cudaMemcpyDeviceToHost, s);
   if (!err) err = (int)cudaMemcpyAsync(ipiv, di.p + 1, (size_t)size * sizeof(int), cudaMemcpyDeviceToHost, s);
   if (!err) err = (int)cudaStreamSynchronize(s);
-  if (!err && !dev_a) err = stage_out(st, 2, a, *plda, m, n, es, dlda);
+  if (!err && !dev_a) err = stage_out(lease.st(), 2, a, *plda, m, n, es, dlda);
   if (err) { cudaDeviceSynchronize(); fail(err); int e = -1; *info = -1; return xerbla_(k_getrf_names[type], &e, 6); }
   *info = (hinfo == INT_MAX) ? 0 : hinfo;   // first exactly-zero pivot, 1-based (lu.cpp:38-39)
   return 0;
@@ -1135,7 +894,8 @@ int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, c
   load_scalar(type, beta, p.beta);
   p.A = dA; p.lda = lda; p.B = dB; p.ldb = ldb; p.C = dC; p.ldc = ldc;
   t_error[0] = 0;
-  const int err = run_device(p, (cudaStream_t)stream, variant);
+  const int err = (variant == B200BLAS_AUTO && multi_wanted(p)) ? fail(multi_gemm(p, false, (cudaStream_t)stream, nullptr, nullptr))
+                                                               : run_device(p, (cudaStream_t)stream, variant);
   if (err) { info = -1; return xerbla_(k_names[type], &info, 6); }
   return 0;
 }
@@ -1153,7 +913,7 @@ const char* b200blas_last_variant(void) { return t_variant; }
 uint64_t b200blas_kernel_launches(void) { return g_launches.load(); }
 void b200blas_set_variant(int variant) { g_forced_variant.store(variant == B200BLAS_AUTO ? -1 : variant); }
 void b200blas_last_transfer(uint64_t* h2d, uint64_t* d2h) { if (h2d) *h2d = t_h2d; if (d2h) *d2h = t_d2h; }
-void b200blas_release(void) { std::lock_guard<std::mutex> lock(g_stage.mu); g_stage.release(); }
+void b200blas_release(void) { staging_pool().free_idle(); multi_release(); }
 double b200blas_pipe_peak(int pipe, int millis) { return pipe_peak(pipe, millis); }
 
 }  // extern "C"

@@ -231,10 +231,12 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
 template <typename T, int NBP>
 __global__ void __launch_bounds__(256)
 getf2_panel_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, int64_t lda, int* __restrict__ ipiv, int64_t row_base,
-                   int* __restrict__ info, int64_t col_base, unsigned char* __restrict__ scratch) {
+                   int* __restrict__ info, int64_t col_base, unsigned char* __restrict__ scratch, T* __restrict__ gslab) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* slab = reinterpret_cast<T*>(smem_raw);   // slab[r * (NBP + 1) + c]
   constexpr int LDS = NBP + 1;
+  // slab[r * (NBP + 1) + c]: shared memory, or -- panels too tall for G slabs of shared memory (m above ~120k rows
+  // for double) -- this CTA's stretch of a global scratch buffer (L2-resident; slower, but no row limit)
+  T* slab = gslab ? gslab + (size_t)blockIdx.x * (size_t)rows_per_cta * LDS : reinterpret_cast<T*>(smem_raw);
   __shared__ T prow[NBP], krow[NBP];
   __shared__ double red_score[8];
   __shared__ int red_row[8], red_w[8];
@@ -554,6 +556,7 @@ struct GetrfCtx {
   int sms = 0;
   int* src_top = nullptr; int* disp_dst = nullptr; int* disp_src = nullptr; int* disp_count = nullptr; int* idx_global = nullptr;
   unsigned char* panel_scratch = nullptr;
+  void* gslab = nullptr;   // global-memory slab for panels taller than shared memory holds (nullptr: not needed)
   void* W = nullptr; size_t w_bytes = 0;
   size_t max_dyn_smem = 0;
 };
@@ -619,11 +622,17 @@ int launch_panel(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t 
       return 0;
     }   // taller than 16 CTAs' shared memory: the cooperative-grid kernel below
   }
-  int G = (int)std::min<int64_t>(cx.sms, (mrows + 255) / 256);   // about one panel row per thread; G <= 256 (candidate reduce)
+  // about one panel row per thread; the candidate reduce reads one candidate per thread, so G <= 256 CTAs
+  int G = (int)std::min<int64_t>(std::min(cx.sms, 256), (mrows + 255) / 256);
   if (G < 1) G = 1;
   int rows_per_cta = (int)((mrows + G - 1) / G);
-  const size_t smem = (size_t)rows_per_cta * (NBP + 1) * sizeof(T);
-  if (smem + 4096 > cx.max_dyn_smem) return (int)cudaErrorInvalidConfiguration;   // panel taller than ~120k rows
+  size_t smem = (size_t)rows_per_cta * (NBP + 1) * sizeof(T);
+  T* gslab = nullptr;
+  if (smem + 4096 > cx.max_dyn_smem) {   // taller than G slabs of shared memory: the slab moves to global memory
+    if (!cx.gslab) return (int)cudaErrorInvalidConfiguration;
+    gslab = (T*)cx.gslab;
+    smem = 0;
+  }
   B200_SET_MAX_DYN_SMEM_ONCE((getf2_panel_kernel<T, NBP>), cx.max_dyn_smem - 4096);   // the largest slab any panel may need
   B200_CUDA_TRY(cudaMemsetAsync(cx.panel_scratch, 0, 64, s));
   T* A = (T*)p.A + j0 + j0 * p.lda;
@@ -633,7 +642,7 @@ int launch_panel(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t 
   int* info = p.dinfo;
   unsigned char* scratch = cx.panel_scratch;
   int64_t mr = mrows;
-  void* args[] = {&mr, &nb, &rows_per_cta, &A, &lda, &ipiv, &row_base, &info, &col_base, &scratch};
+  void* args[] = {&mr, &nb, &rows_per_cta, &A, &lda, &ipiv, &row_base, &info, &col_base, &scratch, &gslab};
   B200_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)getf2_panel_kernel<T, NBP>, dim3(G), dim3(256), args, smem, s));
   count_launch();
   return 0;
@@ -684,13 +693,20 @@ int getrf_typed(const GetrfProblem& p, cudaStream_t s) {
   cx.w_bytes = std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)1 << 20, (size_t)size * (size_t)p.n * sizeof(T)));
   // a gather chunk must hold at least one column of `size / 2` rows
   cx.w_bytes = std::max(cx.w_bytes, (size_t)size * sizeof(T));
-  const size_t total = (ints * sizeof(int) + 255) / 256 * 256 + (ps + 255) / 256 * 256 + cx.w_bytes;
+  // tall panels (the first panel is the tallest): G slabs of shared memory hold G * (optin - 4096) bytes
+  constexpr int NBP = Leaf<T>::NB;
+  const int gmax = std::min(cx.sms, 256);
+  const int64_t rpc0 = (p.m + gmax - 1) / gmax;
+  size_t gslab_bytes = 0;
+  if ((size_t)rpc0 * (NBP + 1) * sizeof(T) + 4096 > cx.max_dyn_smem) gslab_bytes = (size_t)gmax * (size_t)rpc0 * (NBP + 1) * sizeof(T);
+  const size_t total = (ints * sizeof(int) + 255) / 256 * 256 + (ps + 255) / 256 * 256 + (cx.w_bytes + 255) / 256 * 256 + gslab_bytes;
   unsigned char* ws = nullptr;
   B200_CUDA_TRY(cudaMallocAsync((void**)&ws, total, s));
   int* ip = (int*)ws;
   cx.src_top = ip; cx.disp_dst = ip + size; cx.disp_src = ip + 2 * size; cx.disp_count = ip + 3 * size; cx.idx_global = ip + 3 * size + 16;
   cx.panel_scratch = ws + (ints * sizeof(int) + 255) / 256 * 256;
   cx.W = cx.panel_scratch + (ps + 255) / 256 * 256;
+  if (gslab_bytes) cx.gslab = (unsigned char*)cx.W + (cx.w_bytes + 255) / 256 * 256;
   int e = getrf_rec<T>(p, cx, 0, size, s);
   if (!e && p.n > size) {   // wide matrix: the columns right of the square part (LAPACK semantics)
     e = apply_pivots<T>(p, cx, 0, size, size, p.n - size, s);

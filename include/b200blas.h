@@ -1,8 +1,9 @@
 /* include/b200blas.h -- C ABI of libb200blas.so, the sm_100a (NVIDIA B200) GEMM engine behind Eigen's BLAS seams.
  *
  * Section 1 is the drop-in boundary: exactly the symbols the reference binds for its dense matrix-matrix
- * product hot path.  Section 2 is the device-resident surface the benchmark and the multi-GPU driver use (the
- * reference has no device API for this path).  Plain C types only -- no CUDA or torch types.
+ * product hot path.  Section 2 is the device-resident surface the benchmark uses (the reference has no device API for
+ * this path).  Section 3 is the multi-GPU partitioner that sits behind sections 1 and 2.
+ * Plain C types only -- no CUDA or torch types.
  *
  * Reference interfaces replaced (paths relative to the PX4/eigen tree):
  *   Eigen/src/misc/blas.h:347-352                  prototypes of sgemm_/dgemm_/cgemm_/zgemm_
@@ -152,6 +153,63 @@ void b200blas_set_variant(int variant);       /* process-wide override; B200BLAS
 void b200blas_last_transfer(uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* release cached device workspaces / pinned staging buffers */
 void b200blas_release(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 3. Multi-GPU partitioner behind the same entry points (the B200 counterpart of parallelize_gemm,
+ *    Eigen/src/Core/products/Parallelizer.h:85-157, invoked from GeneralMatrixMatrix.h:483-489: the caller writes
+ *    one product and gets all workers).  ONE process drives N devices: C is cut into a pr x pc grid of tiles (2 -> 1x2,
+ *    4 -> 2x2, 8 -> 2x4; k is never split, so there is no reduction), device (i,j) needs the row panel A_i and the column
+ *    panel B_j.  Every k-chunk of a panel crosses the slow link ONCE (PCIe for host operands, the root's NVLink egress
+ *    for device operands) to one "owner" device of its grid row / column and is relayed to the other devices of that
+ *    row / column by peer-to-peer copy-engine transfers (no SMs involved); the products on the chunks that have landed
+ *    overlap the transfers of the later ones; finished column sub-slabs of the C tiles flow back while the last
+ *    products run (beta*C is folded in by a small kernel, or not read at all when beta == 0).
+ *    Enabled by the environment variable B200BLAS_NGPUS=N or b200blas_set_devices(N); then ?gemm_ on host pointers,
+ *    ?gemm_ on device pointers (operands resident on the current device = "root") and b200blas_gemm_dev use N devices
+ *    for products of at least B200BLAS_MULTI_MIN_FLOPS (default 4.6e11 = 2*6144^3) flops; smaller ones stay on one GPU.
+ *    B200BLAS_GRID=PRxPC / b200blas_set_grid override the grid.
+ * ------------------------------------------------------------------------------------------------------------ */
+int b200blas_set_devices(int n);              /* n <= 1: single device.  Returns the device count in effect (clamped to the visible devices) */
+int b200blas_get_devices(void);
+int b200blas_set_grid(int pr, int pc);        /* 0,0 restores the default grid; returns 0, or -1 if pr*pc does not match the device count */
+/* page-lock / unlock caller memory so that every device can DMA it directly (cudaHostRegister, portable).  Optional:
+ * pageable operands work (they are staged through pinned rings by copy threads), registered ones are faster. */
+int b200blas_host_register(void* p, uint64_t bytes);
+int b200blas_host_unregister(void* p);
+
+/* The partition plan as data (pure host arithmetic; used by the executor, by tests/test_multi_plan.py -- which
+ * interprets it on the CPU -- and by bench.py for reporting).  Regions are in elements of the scalar type, in the
+ * column-major coordinates of their buffer. */
+typedef struct {
+  int loc;                 /* -1: the caller's operand ("origin": host memory, or the root device's memory); d >= 0: device d of the plan */
+  int buf;                 /* origin: 0 = A, 1 = B, 2 = C.  device: 0 = panel A_i, 1 = panel B_j, 2 = product tile P, 3 = uploaded C tile,
+                              4 + s = (root only) tile received from device s */
+  int64_t r0, c0, rows, cols;
+} b200blas_region;
+enum { B200BLAS_STEP_COPY = 0, B200BLAS_STEP_GEMM = 1, B200BLAS_STEP_AXPBY = 2 };
+typedef struct {
+  int kind;                /* COPY: z := x.  GEMM: z := alpha*op(x)*op(y) + beta*z.  AXPBY: z := beta*z + alpha*x */
+  int dev, stream;         /* issuing device (plan index) and stream slot: 0 fetch, 1 relay, 2 compute, 3 return, 4 fold */
+  b200blas_region x, y, z;
+  int opa, opb;            /* 0 = N, 1 = T, 2 = C */
+  double alpha[2], beta[2];
+  int nwait, wait[4];      /* steps (earlier in the list, other streams) that must have completed */
+  int record;              /* some later step waits on this one */
+} b200blas_step;
+enum { B200BLAS_PLAN_MAXDEV = 8, B200BLAS_PLAN_MAXCHUNK = 64 };
+typedef struct {
+  int ndev, pr, pc, nchunks, ngroups, host_origin;
+  int64_t row_cut[B200BLAS_PLAN_MAXDEV + 1], col_cut[B200BLAS_PLAN_MAXDEV + 1], k_cut[B200BLAS_PLAN_MAXCHUNK + 1];
+  int group_first_chunk[B200BLAS_PLAN_MAXCHUNK + 1];
+  int64_t ld[B200BLAS_PLAN_MAXDEV][4];      /* leading dimensions of the device buffers 0..3 (4 + s uses ld[s][2]) */
+  int64_t elems[B200BLAS_PLAN_MAXDEV][4];   /* their sizes in elements (0: not used on that device) */
+  int nsteps;
+} b200blas_plan_info;
+/* Builds the plan of one product.  host_origin: 1 = operands in host memory, 0 = resident on device 0 of the plan.
+ * pr = pc = 0: default grid.  Returns the number of steps (written to steps[0 .. min(cap, nsteps)) ), or -1. */
+int b200blas_multi_plan(int type, char transa, char transb, int64_t m, int64_t n, int64_t k, const double* alpha2,
+                        const double* beta2, int64_t lda, int64_t ldb, int64_t ldc, int ndev, int pr, int pc,
+                        int host_origin, b200blas_plan_info* info, b200blas_step* steps, int cap);
 
 /* Pipe-peak micro-benchmarks (register-resident loops, no memory traffic) used as roofline denominators:
  * pipe 0 = FP64 DMMA (mma.sync.m8n8k4.f64), 1 = FP64 DFMA, 2 = FP32 FFMA, 3 = TF32 tcgen05.mma (dense).

@@ -238,3 +238,119 @@ def test_pageable_large_operands_go_through_the_staging_ring(L):
         assert oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "T" if False else "N", m, n, k, 0.7, A, m + 5, B, k + 3, 1.3, c, m + 7) == 0
         assert c[m:].tobytes() == C0[m:].tobytes()
         _check(t, "N", "N", m, n, k, 0.7, 1.3, A, B, C0, c, m + 7, port_too=False)
+
+
+# ---- round 2: the default LARGE-shape kernels on ragged shapes (VERDICT r1 "what's weak" 1 and 2) ------------------------
+PAIR_SHAPES = [(1537, 2049, 1000), (2051, 1283, 4099), (777, 2600, 333)]
+
+
+def _sample_rows(m, count=20):
+    """First / last rows, both sides of every 128- and 256-row tile edge near the ends, and a spread in between."""
+    edge = [0, 1, 127, 128, 255, 256, m - 257, m - 256, m - 129, m - 128, m - 2, m - 1]
+    mid = list(np.linspace(0, m - 1, count).astype(int))
+    return np.array(sorted({r for r in edge + mid if 0 <= r < m}), dtype=np.int32)
+
+
+def _dev_matrix(torch, host):
+    """An (ld x cols) F-ordered numpy array as a device tensor with the same column-major bytes."""
+    return torch.from_numpy(np.ascontiguousarray(host.T)).cuda()
+
+
+@pytest.mark.parametrize("t", list("sc"))
+def test_cta_pair_kernels_ragged_shapes_all_ops(L, t):
+    """The CTA-pair tcgen05 kernels (the default for m, n >= 512) on shapes that are multiples of nothing: ragged
+    m / n / k (TMA out-of-bounds fill, row < m, ncol clipping, the 128-row B halves of a ragged last pair tile), all
+    nine op pairs, ld = dim + 1, the xBLAT alpha / beta grid incl. beta = 0 with NaN in C, untouched padding rows --
+    through ?gemm_ on host arrays AND b200blas_gemm_dev on device pointers (dblat3.f:395-675 semantics)."""
+    import torch
+    rng = np.random.default_rng(4321)
+    cplx = t == "c"
+    alphas = [1.0, (0.7 - 0.9j) if cplx else 0.7, -1.0]
+    betas = [1.0, (1.3 - 1.1j) if cplx else 1.3, 0.0]
+    ops = [(x, y) for x in "NTC" for y in "NTC"]
+    worst = 0.0
+    for si, (m, n, k) in enumerate(PAIR_SHAPES):
+        rows = _sample_rows(m)
+        for oi, (ta, tb) in enumerate(ops):
+            ra, ca = (m, k) if ta == "N" else (k, m)
+            rb, cb = (k, n) if tb == "N" else (n, k)
+            A = oa.rand_matrix(rng, t, ra, ca, ld=ra + 1)
+            B = oa.rand_matrix(rng, t, rb, cb, ld=rb + 1)
+            ldc = m + 1
+            C0 = oa.rand_matrix(rng, t, m, n, ld=ldc)
+            al, be = alphas[(si + oi) % 3], betas[(si + 2 * oi) % 3]
+            if be == 0.0:
+                C0[:m] = np.nan  # beta == 0 must not read C (blas/level3_impl.h:64)
+            Cin = C0 if be != 0.0 else np.zeros_like(C0)
+            # (1) F77 entry, host arrays
+            c = C0.copy(order="F")
+            # (the host path cuts C into column slabs, so it reaches the pair kernels only for its widest slabs)
+            assert oa.call_gemm(getattr(L, t + "gemm_"), t, ta, tb, m, n, k, al, A, ra + 1, B, rb + 1, be, c, ldc) == 0, eigen_b200.last_error()
+            assert c[m:].tobytes() == C0[m:].tobytes(), "padding row of C was touched (host path)"
+            _, ratio = _check(t, ta, tb, m, n, k, al, be, A, B, Cin, c, ldc, rows=rows, port_too=False)
+            worst = max(worst, ratio)
+            # (2) device pointers with the caller's odd leading dimensions
+            dA, dB, dC = _dev_matrix(torch, A), _dev_matrix(torch, B), _dev_matrix(torch, C0)
+            assert eigen_b200.gemm_dev(t, ta, tb, m, n, k, al, dA, ra + 1, dB, rb + 1, be, dC, ldc) == 0, eigen_b200.last_error()
+            torch.cuda.synchronize()
+            assert "pair" in eigen_b200.last_variant(), eigen_b200.last_variant()
+            c2 = np.asfortranarray(dC.cpu().numpy().T)
+            assert c2[m:].tobytes() == C0[m:].tobytes(), "padding row of C was touched (device path)"
+            _, ratio = _check(t, ta, tb, m, n, k, al, be, A, B, Cin, c2, ldc, rows=rows, port_too=False)
+            worst = max(worst, ratio)
+    print("pair kernels, worst gauge ratio", t, worst)
+
+
+@pytest.mark.parametrize("t", list("dz"))
+def test_dmma_loader_modes_on_odd_device_pointers(L, t):
+    """Device-pointer products whose operands are sub-blocks at ODD row / column offsets of matrices with ODD leading
+    dimensions (what &lu(k+bs, k+bs) is): 8-byte aligned, not 16 -> the 8-byte cp.async loader (LD_DIM8); transposed
+    operands -> LD_K; aligned even ones -> LD_DIM16.  More than 100 big tiles so the 128x64 configuration runs; every
+    (A mode) x (B mode) combination of the real kernel, and the complex ones."""
+    import torch
+    rng = np.random.default_rng(2468)
+    cplx = t == "z"
+    m, n, k = (1500, 1100, 301) if not cplx else (801, 600, 203)
+    want_variant = "dmma_z_64x32x16_w16x16_2cta_mbar" if cplx else "dmma_d_128x64x16_w32x32_2cta_mbar"
+    es = 16 if cplx else 8
+    rows = _sample_rows(m, 12)
+    # (row offset, column offset, ld parity): odd offsets + odd ld -> 8-byte aligned only; (0, 0, even) -> 16-byte aligned
+    layouts = [(1, 3, 1), (0, 0, 0), (3, 1, 1)]
+    al, be = ((0.7 - 0.9j), (1.3 - 1.1j)) if cplx else (0.7, 1.3)
+    worst = 0.0
+    for ta in "NTC":
+        for tb in "NTC":
+            for li, (ro, co, odd) in enumerate(layouts):
+                if cplx and li == 2:
+                    continue
+                ra, ca = (m, k) if ta == "N" else (k, m)
+                rb, cb = (k, n) if tb == "N" else (n, k)
+
+                def parent(r, c_):
+                    ld = r + ro + 2
+                    ld += (ld % 2 == 0) if odd else (ld % 2 == 1)   # odd / even leading dimension
+                    return oa.rand_matrix(rng, t, ld, c_ + co), ld
+
+                PA, lda = parent(ra, ca)
+                PB, ldb = parent(rb, cb)
+                PC, ldc = parent(m, n)
+                PC0 = PC.copy(order="F")
+                dA, dB, dC = _dev_matrix(torch, PA), _dev_matrix(torch, PB), _dev_matrix(torch, PC)
+                off = lambda ld: (ro + co * ld) * es  # noqa: E731
+                r = eigen_b200.gemm_dev(t, ta, tb, m, n, k, al, dA.data_ptr() + off(lda), lda, dB.data_ptr() + off(ldb), ldb,
+                                        be, dC.data_ptr() + off(ldc), ldc)
+                assert r == 0, eigen_b200.last_error()
+                torch.cuda.synchronize()
+                assert eigen_b200.last_variant() == want_variant, eigen_b200.last_variant()
+                got = np.asfortranarray(dC.cpu().numpy().T)
+                # everything outside the m x n window is bit-identical
+                mask = np.ones(PC0.shape, dtype=bool)
+                mask[ro:ro + m, co:co + n] = False
+                assert np.array_equal(got[mask], PC0[mask]), "elements outside the C window were modified"
+                Asub = np.asfortranarray(PA[ro:, co:co + ca])
+                Bsub = np.asfortranarray(PB[ro:, co:co + cb])
+                Csub = np.asfortranarray(PC0[ro:, co:co + n])
+                gsub = np.asfortranarray(got[ro:, co:co + n])
+                _, ratio = _check(t, ta, tb, m, n, k, al, be, Asub, Bsub, Csub, gsub, Csub.shape[0], rows=rows, port_too=False)
+                worst = max(worst, ratio)
+    print("dmma loader modes, worst gauge ratio", t, worst)
