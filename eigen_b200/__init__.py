@@ -198,9 +198,9 @@ def multi_plan(t, transa, transb, m, n, k, alpha, beta, ndev, grid=(0, 0), host_
     al = (C.c_double * 2)(complex(alpha).real, complex(alpha).imag)
     be = (C.c_double * 2)(complex(beta).real, complex(beta).imag)
     info = PlanInfo()
-    steps = (Step * cap)()
+    steps = (Step * max(cap, 1))()
     ns = lib().b200blas_multi_plan(TYPE_CODE[t], transa.encode(), transb.encode(), m, n, k, al, be, 0, 0, 0, ndev, grid[0], grid[1],
                                    1 if host_origin else 0, C.byref(info), steps, cap)
-    if ns < 0 or ns > cap:
+    if ns < 0 or (cap > 0 and ns > cap):
         raise ValueError("b200blas_multi_plan failed (%d)" % ns)
-    return info, [steps[i] for i in range(ns)]
+    return info, [steps[i] for i in range(min(ns, cap))]

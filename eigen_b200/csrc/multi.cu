@@ -684,9 +684,9 @@ int execute(const GemmProblem& p, bool host_origin, cudaStream_t user_stream, ui
   return 0;
 }
 
-double min_flops() {
-  static const double v = [] { const char* e = getenv("B200BLAS_MULTI_MIN_FLOPS"); return e ? atof(e) : 4.6e11; }();
-  return v;
+double min_flops() {   // read on every call (only reached when more than one device is enabled): tests lower it at run time
+  const char* e = getenv("B200BLAS_MULTI_MIN_FLOPS");
+  return e ? atof(e) : 4.6e11;
 }
 
 }  // namespace

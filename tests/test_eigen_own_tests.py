@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "oracle", "_ref")
 
 
-def _run(name, variant, seed):
+def _run(name, variant, seed, ngpus=1):
     exe = os.path.join(BIN, "eigen_test_" + name)
     if not os.path.exists(exe):
         pytest.skip("oracle/_ref/eigen_test_%s not built (make -C oracle eigen_tests needs /root/reference)" % name)
@@ -23,6 +23,11 @@ def _run(name, variant, seed):
     env.pop("B200BLAS_VARIANT", None)
     if variant != "auto":
         env["B200BLAS_VARIANT"] = variant
+    if ngpus > 1:
+        # the multi-GPU partitioner behind the same dgemm_ (include/b200blas.h section 3).  The products of these tests are
+        # small, so the size threshold is lowered to route ALL of them through it; with fewer physical GPUs than plan
+        # devices the plan devices share the GPUs (B200BLAS_MULTI_VIRTUAL), which runs the same executor.
+        env.update(B200BLAS_NGPUS=str(ngpus), B200BLAS_MULTI_MIN_FLOPS="0", B200BLAS_MULTI_VIRTUAL="1")
     # r<repeat> s<seed>: test/main.h:136,766-780
     p = subprocess.run([exe, "r3", "s%d" % seed], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900, text=True)
     assert p.returncode == 0, p.stdout[-3000:]
@@ -39,3 +44,10 @@ def test_eigen_product_tests_pass_on_the_gpu_library(name, variant):
 def test_eigen_solver_tests_pass_on_the_gpu_library(name):
     """Binaries import ?trsm_/?trmm_/?gemm_ from libb200blas.so (nm -D); ?gemv_/?trmv_ come from the reference blas."""
     _run(name, "auto", 4242)
+
+
+@pytest.mark.parametrize("name", ["product_large", "product_extra", "lu"])
+def test_eigen_tests_pass_with_the_multi_gpu_partitioner(name):
+    """the reference's own tests, unmodified, with B200BLAS_NGPUS=8 -- every product is cut into the
+    2x4 grid inside dgemm_ (Parallelizer.h:85-157 is what the reference does at this point)."""
+    _run(name, "auto", 777, ngpus=8)
