@@ -18,6 +18,7 @@
 #include <climits>
 #include <cooperative_groups.h>
 #include <cstdlib>
+#include <type_traits>
 
 #include "../../include/b200blas.h"
 #include "common.cuh"
@@ -162,6 +163,224 @@ __global__ void __launch_bounds__(256) potf2_cta_kernel(int upper, int d, int64_
       if (upper) A[j + (int64_t)i * lda] = Sc<T>::conj(S[i][j]); else A[i + (int64_t)j * lda] = S[i][j];
     }
   }
+}
+
+// ---- Cholesky of one diagonal block of order <= NBL (128; 64 for complex double) by ONE CTA -----------------------------------
+// The block (lower-canonical: element (i, j) = A(i,j) for uplo = L, conj(A(j,i)) for uplo = U) lives in shared memory.
+// It is factored in panels of 32 columns: thread t owns row c0 + t of the panel in 32 registers; a column costs ONE
+// __syncthreads -- the raw (unscaled) entries of the diagonal rows are published, every thread derives the pivot root
+// and the scaled multipliers from them itself -- and the part of the block right of the panel is then updated by all
+// 256 threads with 4 x 4 register tiles (rows / columns interleaved so that every shared-memory access is conflict
+// free).  Rows / columns past d are the identity, so the unrolled loops are valid for every d <= NBL.
+template <typename T> struct Blk { static constexpr int NBL = 128; };
+template <> struct Blk<double2> { static constexpr int NBL = 64; };
+
+template <typename T, int NBL>
+__global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int64_t d0, T* __restrict__ A, int64_t lda, int* __restrict__ info) {
+  using R = typename Sc<T>::real;
+  constexpr int LDS = NBL + 1;
+  extern __shared__ __align__(16) unsigned char blk_smem[];
+  T* S = reinterpret_cast<T*>(blk_smem);   // S[i * LDS + j], i >= j
+  __shared__ T colbuf[2][32];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < NBL * NBL; idx += 256) {
+    int i, j;
+    if (upper) { j = idx % NBL; i = idx / NBL; } else { i = idx % NBL; j = idx / NBL; }   // coalesced either way
+    T v = (i == j) ? sc_one<T>() : Sc<T>::zero();
+    if (i < d && j <= i) v = upper ? Sc<T>::conj(A[j + (int64_t)i * lda]) : A[i + (int64_t)j * lda];
+    S[i * LDS + j] = v;
+  }
+  __syncthreads();
+  bool ok = true;   // uniform over the CTA
+  for (int c0 = 0; c0 < NBL && c0 < d && ok; c0 += 32) {
+    const int t = tid;
+    const bool rowact = t < NBL - c0;
+    T a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = rowact ? S[(c0 + t) * LDS + c0 + j] : Sc<T>::zero();
+    if (t < 32) colbuf[0][t] = a[0];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      if (ok) {
+        const R x = sc_real<T>(colbuf[k & 1][k]);
+        if (x <= (R)0) {   // a NaN pivot continues, as in the reference (LLT.h:316-317)
+          if (tid == 0) atomicMin(info, (int)(d0 + c0 + k + 1));
+          ok = false;
+        } else {
+          R l, rl;
+          pivot_roots(x, l, rl);
+          if (t == k) a[k] = sc_from_real<T>(l);
+          else if (t > k) {
+            a[k] = sc_scale<T>(a[k], rl);
+#pragma unroll
+            for (int j = k + 1; j < 32; ++j) {
+              const T ljk = sc_scale<T>(colbuf[k & 1][j], rl);   // L(c0 + j, c0 + k)
+              sc_fnma<T>(a[j], a[k], Sc<T>::conj(ljk));
+            }
+          }
+          if (k + 1 < 32) {
+            if (t < 32 && t > k) colbuf[(k + 1) & 1][t] = a[k + 1];
+            __syncthreads();
+          }
+        }
+      }
+    }
+    if (rowact) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (t >= 32 || j <= t) S[(c0 + t) * LDS + c0 + j] = a[j];
+    }
+    __syncthreads();
+    const int c1 = c0 + 32;
+    if (!ok || c1 >= NBL || c1 >= d) continue;
+    // S[i][j] -= sum_k L[i][c0 + k] conj(L[j][c0 + k]) for i >= j >= c1 (identity rows past d have zero L entries)
+    const int nt = (NBL - c1) / 4;
+    for (int tile = tid; tile < nt * nt; tile += 256) {
+      const int ti = tile / nt, tj = tile % nt;
+      T acc[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = c1 + ti + r * nt, j = c1 + tj + c * nt;
+          acc[r][c] = (i >= j) ? S[i * LDS + j] : Sc<T>::zero();
+        }
+      const T* li = S + (c1 + ti) * LDS + c0;
+      const T* lj = S + (c1 + tj) * LDS + c0;
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        T vi[4], vj[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { vi[r] = li[r * nt * LDS + k]; vj[r] = Sc<T>::conj(lj[r * nt * LDS + k]); }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) sc_fnma<T>(acc[r][c], vi[r], vj[c]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int i = c1 + ti + r * nt, j = c1 + tj + c * nt;
+          if (i >= j) S[i * LDS + j] = acc[r][c];
+        }
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < NBL * NBL; idx += 256) {
+    int i, j;
+    if (upper) { j = idx % NBL; i = idx / NBL; } else { i = idx % NBL; j = idx / NBL; }
+    if (i < d && j <= i) {
+      const T v = S[i * LDS + j];
+      if (upper) A[j + (int64_t)i * lda] = Sc<T>::conj(v); else A[i + (int64_t)j * lda] = v;
+    }
+  }
+}
+
+// ---- auxiliary stream + events of the look-ahead factorizations (one set per host thread and device) -------------------------
+struct LookAhead {
+  cudaStream_t sp = nullptr;   // panel chain, highest priority: its small kernels slip in between the CTAs of the big update
+  cudaEvent_t e_in = nullptr, e_panel = nullptr, e_rest = nullptr, e_out = nullptr;
+  int dev = -1;
+  int init() {
+    int cur = 0;
+    B200_CUDA_TRY(cudaGetDevice(&cur));
+    if (sp && dev == cur) return 0;
+    release();
+    int lo = 0, hi = 0;
+    B200_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    B200_CUDA_TRY(cudaStreamCreateWithPriority(&sp, cudaStreamNonBlocking, hi));
+    for (cudaEvent_t* e : {&e_in, &e_panel, &e_rest, &e_out}) B200_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    dev = cur;
+    return 0;
+  }
+  void release() {
+    if (sp) cudaStreamDestroy(sp);
+    for (cudaEvent_t* e : {&e_in, &e_panel, &e_rest, &e_out}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+    sp = nullptr; dev = -1;
+  }
+};
+thread_local LookAhead t_look;
+
+bool lookahead_enabled() {
+  static const bool v = [] { const char* e = getenv("B200BLAS_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
+// C[r0.., c0..] -= L[r0.., j..j+jb) * L[c0.., j..j+jb)^H in lower-canonical coordinates (r0 == c0: only the referenced
+// triangle of the window is touched); for uplo = U the same update on the stored transpose.
+template <typename T>
+int potrf_update(const PotrfProblem& p, int64_t j, int64_t jb, int64_t r0, int64_t nr, int64_t c0, int64_t nc, cudaStream_t s) {
+  if (nr <= 0 || nc <= 0) return 0;
+  const bool cplx = sizeof(T) != sizeof(typename Sc<T>::real);
+  T* A = (T*)p.A;
+  GemmProblem g;
+  g.type = p.type; g.alpha[0] = -1.0; g.alpha[1] = 0.0; g.beta[0] = 1.0; g.beta[1] = 0.0;
+  g.k = jb; g.uplo = p.uplo; g.herm = cplx ? 1 : 0; g.lda = g.ldb = g.ldc = p.lda;
+  if (p.uplo != UPLO_UPPER) {
+    g.opa = OP_N; g.opb = OP_C; g.m = nr; g.n = nc;
+    g.A = A + r0 + j * p.lda; g.B = A + c0 + j * p.lda; g.C = A + r0 + c0 * p.lda;
+  } else {
+    g.opa = OP_C; g.opb = OP_N; g.m = nc; g.n = nr;
+    g.A = A + j + c0 * p.lda; g.B = A + j + r0 * p.lda; g.C = A + c0 + r0 * p.lda;
+  }
+  return run_gemm_device(g, s, B200BLAS_AUTO);
+}
+
+// Right-looking blocked Cholesky with one step of look-ahead (the blocked loop of LLT.h:330-360 with blockSize = NBL):
+//   panel chain (stream sp):  factor A11 (one CTA) -> A21 := A21 L11^-H (one substitution-leaf launch) -> update of the NEXT
+//                             block column only -> factor the next A11 ...
+//   bulk (the caller's stream): A22 -= A21 A21^H on everything right of the next block column ("bottleneck", LLT.h:357),
+// so that the latency-bound panel chain of step j+1 runs underneath the tensor-pipe update of step j.
+template <typename T>
+int potrf_blocked(const PotrfProblem& p, cudaStream_t s) {
+  constexpr int NBL = Blk<T>::NBL;
+  const bool upper = p.uplo == UPLO_UPPER;
+  T* A = (T*)p.A;
+  const int64_t n = p.n;
+  constexpr size_t smem = (size_t)NBL * (NBL + 1) * sizeof(T);
+  B200_SET_MAX_DYN_SMEM_ONCE((potf2_block_kernel<T, NBL>), smem);
+  const bool look = lookahead_enabled() && n > 4 * NBL;
+  cudaStream_t sp = s;
+  LookAhead& la = t_look;
+  if (look) {
+    B200_CUDA_TRY(la.init());
+    sp = la.sp;
+    B200_CUDA_TRY(cudaEventRecord(la.e_in, s));
+    B200_CUDA_TRY(cudaStreamWaitEvent(sp, la.e_in, 0));
+  }
+  bool rest_pending = false;
+  for (int64_t j = 0; j < n; j += NBL) {
+    const int64_t jb = std::min<int64_t>(NBL, n - j), n2 = n - j - jb;
+    potf2_block_kernel<T, NBL><<<1, 256, smem, sp>>>(upper ? 1 : 0, (int)jb, j, A + j + j * p.lda, p.lda, p.dinfo);
+    count_launch();
+    B200_CUDA_TRY(cudaGetLastError());
+    if (n2 <= 0) break;
+    TriProblem t;   // A21 := A21 * L11^-H  /  A12 := U11^-H * A12   (LLT.h:356)
+    t.type = p.type; t.uplo = p.uplo; t.op = OP_C; t.unit = 0; t.alpha[0] = 1.0; t.alpha[1] = 0.0;
+    t.A = A + j + j * p.lda; t.lda = p.lda; t.ldb = p.lda;
+    if (!upper) { t.left = 0; t.m = n2; t.n = jb; t.B = A + (j + jb) + j * p.lda; }
+    else { t.left = 1; t.m = jb; t.n = n2; t.B = A + j + (j + jb) * p.lda; }
+    B200_CUDA_TRY(launch_trsm(t, sp));
+    const int64_t r1 = j + jb, nb2 = std::min<int64_t>(NBL, n2), r2 = r1 + nb2, n3 = n - r2;
+    if (look) {
+      B200_CUDA_TRY(cudaEventRecord(la.e_panel, sp));
+      if (rest_pending) B200_CUDA_TRY(cudaStreamWaitEvent(sp, la.e_rest, 0));   // the previous bulk update also touched the next block column
+    }
+    // next block column: rows r1.., columns [r1, r2)
+    B200_CUDA_TRY(potrf_update<T>(p, j, jb, r1, n2, r1, nb2, sp));
+    if (n3 > 0) {
+      if (look) B200_CUDA_TRY(cudaStreamWaitEvent(s, la.e_panel, 0));
+      B200_CUDA_TRY(potrf_update<T>(p, j, jb, r2, n3, r2, n3, s));
+      if (look) { B200_CUDA_TRY(cudaEventRecord(la.e_rest, s)); rest_pending = true; }
+    }
+  }
+  if (look) {
+    B200_CUDA_TRY(cudaEventRecord(la.e_out, sp));
+    B200_CUDA_TRY(cudaStreamWaitEvent(s, la.e_out, 0));
+  }
+  return 0;
 }
 
 static int64_t split_point(int64_t d, int nb) {
@@ -486,6 +705,170 @@ getf2_cluster_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A,
   cluster.sync();   // nobody exits while a peer may still write into its tables
 }
 
+// ---- LU panel, register resident, on one thread-block cluster (the default leaf for panels of up to 16384 rows) ----------------
+// Every thread owns RPT whole rows of the (<= NBP wide) panel in registers, so the rank-1 update of a column is pure
+// register arithmetic against the pivot row (broadcast from shared memory) -- the shared-memory slab kernels above spend
+// their time in dependent LDS -> DFMA -> STS chains (4.1 us per column measured in round 1 and again under the cluster
+// draft).  Per column: local arg-max (registers, shuffles) -> the CTA's candidate row and, from its owner, row k are
+// pushed into the tables of EVERY CTA of the cluster through distributed shared memory -> one hardware cluster barrier
+// -> identical reduction everywhere -> the owners of rows k / pivot overwrite their registers with each other's row ->
+// scale and update.  Tables are double-buffered by column parity: one cluster barrier per column.
+// compile-time loop: the column index of the register panels must be a constant in every iteration, also where the
+// body is too large for `#pragma unroll` to be honoured (the row arrays would otherwise move to local memory)
+template <int K, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (K < N) {
+    f(std::integral_constant<int, K>{});
+    static_for<K + 1, N>(f);
+  }
+}
+
+template <typename T, int NBP>
+struct RegPanelTables {
+  double score[2][16];
+  int row[2][16];
+  T vals[2][16][NBP];
+  T rowk[2][NBP];
+};
+
+template <typename T, int NBP, int RPT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __restrict__ ipiv, int64_t row_base,
+                 int* __restrict__ info, int64_t col_base) {
+  constexpr int NW = THREADS / 32;
+  __shared__ RegPanelTables<T, NBP> tab;
+  __shared__ double wbest[NW];
+  __shared__ int wrow[NW];
+  __shared__ T myrow[NBP], mykrow[NBP];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cta = (int)cluster.block_rank(), tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  int rq[RPT];
+  T a[RPT][NBP];
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    rq[q] = (cta * RPT + q) * THREADS + tid;
+#pragma unroll
+    for (int c = 0; c < NBP; ++c) a[q][c] = (rq[q] < mrows && c < nb) ? A[rq[q] + (int64_t)c * lda] : Sc<T>::zero();
+  }
+  cluster.sync();   // every CTA's shared memory is live before anybody writes into it remotely
+  const int steps = (int)min((int64_t)nb, mrows);
+  static_for<0, NBP>([&](auto kc) {
+    constexpr int k = decltype(kc)::value;
+    if (k < steps) {
+      constexpr int par = k & 1;
+      // 1. candidate of this thread / warp: largest |a(r,k)| among rows >= k, smallest row on ties (maxCoeff keeps the first)
+      double best = -1.0;
+      int brow = INT_MAX;
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        if (rq[q] >= k && rq[q] < mrows) {
+          const double sc = sc_score<T>(a[q][k]);
+          if (sc > best || (sc == best && rq[q] < brow)) { best = sc; brow = rq[q]; }
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+        const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+        if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
+      }
+      if (lane == 0) { wbest[warp] = best; wrow[warp] = brow; }
+      __syncthreads();
+      // 2. the CTA's candidate (every thread reduces the warp results itself); its owner and the owner of row k publish their rows
+      double cb = -1.0;
+      int crow = INT_MAX;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const double ob = wbest[w];
+        const int orow = wrow[w];
+        if (ob > cb || (ob == cb && orow < crow)) { cb = ob; crow = orow; }
+      }
+      const int krow_cta = k / (RPT * THREADS);   // the CTA that owns row k
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        if (cb >= 0.0 && rq[q] == crow) {
+#pragma unroll
+          for (int c = 0; c < NBP; ++c) myrow[c] = a[q][c];
+        }
+        if (rq[q] == k) {
+#pragma unroll
+          for (int c = 0; c < NBP; ++c) mykrow[c] = a[q][c];
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < CL * NBP; idx += THREADS) {
+        const int peer = idx / NBP, c = idx % NBP;
+        RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, peer);
+        if (cb >= 0.0) rt->vals[par][cta][c] = myrow[c];
+        if (cta == krow_cta) rt->rowk[par][c] = mykrow[c];
+      }
+      if (tid < CL) {
+        RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, tid);
+        rt->score[par][cta] = cb;
+        rt->row[par][cta] = crow;
+      }
+      cluster.sync();   // release / acquire at cluster scope: the remote stores are visible
+      // 3. identical reduction of the CL candidates in every thread
+      double gb = -1.0;
+      int grow = INT_MAX, gw = -1;
+      for (int w = 0; w < CL; ++w) {
+        const double s2 = tab.score[par][w];
+        const int r2 = tab.row[par][w];
+        if (s2 >= 0.0 && (s2 > gb || (s2 == gb && r2 < grow))) { gb = s2; grow = r2; gw = w; }
+      }
+      if (gw < 0) { gb = 0.0; grow = k; }   // a column of NaNs: no candidate compares greater; treated as a zero pivot
+      const int piv = grow;
+      if (cta == 0 && tid == 0) {
+        ipiv[k] = (int)(row_base + piv + 1);
+        if (gb == 0.0) atomicMin(info, (int)(col_base + k + 1));
+      }
+      if (gb != 0.0) {
+        const T* prow = tab.vals[par][gw];
+        // 4. interchange rows k and piv (PartialPivLU.h:384-388): the two owners take over each other's contents
+        if (piv != k) {
+#pragma unroll
+          for (int q = 0; q < RPT; ++q) {
+            if (rq[q] == k) {
+#pragma unroll
+              for (int c = 0; c < NBP; ++c) a[q][c] = prow[c];
+            } else if (rq[q] == piv) {
+#pragma unroll
+              for (int c = 0; c < NBP; ++c) a[q][c] = tab.rowk[par][c];
+            }
+          }
+        }
+        // 5. scale the column below the pivot and update the rest of the panel (PartialPivLU.h:392, :404-405)
+        const T pv = prow[k];
+        T l[RPT];
+        bool act[RPT];
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) {
+          l[q] = Sc<T>::zero();
+          act[q] = rq[q] > k && rq[q] < mrows;
+          if (act[q]) { l[q] = sc_div<T>(a[q][k], pv); a[q][k] = l[q]; }
+        }
+#pragma unroll
+        for (int j = k + 1; j < NBP; ++j) {
+          const T u = prow[j];
+#pragma unroll
+          for (int q = 0; q < RPT; ++q)
+            if (act[q]) sc_fnma<T>(a[q][j], l[q], u);
+        }
+      }
+    }
+  });
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (rq[q] < mrows) {
+#pragma unroll
+      for (int c = 0; c < NBP; ++c)
+        if (c < nb) A[rq[q] + (int64_t)c * lda] = a[q][c];
+    }
+  }
+  cluster.sync();   // nobody exits while a peer may still write into its tables
+}
+
 // ---- row interchanges as a permutation -----------------------------------------------------------------------------------
 // Simulate ipiv[k0 .. k0+ns) (1-based global rows, relative base row_base = k0) on an index array held in shared memory.
 // Output: src_top[k] = source row of destination row k (k < ns), and the list of displaced destinations r >= ns with
@@ -568,10 +951,28 @@ size_t panel_scratch_bytes(int G) {
   return 64 + 2 * ((per + 63) / 64 * 64);
 }
 
-// apply the interchanges ipiv[k0 .. k0+ns) to columns [c0, c0 + ncols) of A (rows k0 .. m)
+// all three steps for ns <= 256 interchanges in ONE launch: a CTA owns whole columns, so reading every source of a column
+// before writing any destination needs only a __syncthreads (the displaced list has at most ns entries)
 template <typename T>
-int apply_pivots(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t ns, int64_t c0, int64_t ncols, cudaStream_t s) {
-  if (ns <= 0 || ncols <= 0) return 0;
+__global__ void __launch_bounds__(256) perm_apply_fused_kernel(int ns, int64_t ncols, const int* __restrict__ src_top, const int* __restrict__ count,
+                                                               const int* __restrict__ dst, const int* __restrict__ src, T* __restrict__ A, int64_t lda) {
+  const int tid = threadIdx.x;
+  const int s_top = tid < ns ? src_top[tid] : -1;
+  int d = -1, sd = 0;
+  if (tid < *count) { d = dst[tid]; sd = src[tid]; }
+  for (int64_t c = blockIdx.x; c < ncols; c += gridDim.x) {
+    T* col = A + c * lda;
+    T vtop = Sc<T>::zero(), vdisp = Sc<T>::zero();
+    if (s_top >= 0) vtop = col[s_top];
+    if (d >= 0) vdisp = col[sd];
+    __syncthreads();
+    if (s_top >= 0 && s_top != tid) col[tid] = vtop;
+    if (d >= 0) col[d] = vdisp;
+  }
+}
+
+// the permutation of the interchanges ipiv[k0 .. k0+ns) (rows k0 .. m) into cx's lists
+inline int build_perm(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t ns, cudaStream_t s) {
   const int64_t mrows = p.m - k0;
   if ((size_t)mrows * sizeof(int) + 2048 <= cx.max_dyn_smem) {
     perm_build_kernel<<<1, 1024, (size_t)mrows * sizeof(int), s>>>(p.dipiv, k0, (int)ns, (int)mrows, cx.src_top, cx.disp_dst, cx.disp_src, cx.disp_count);
@@ -579,8 +980,19 @@ int apply_pivots(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t 
     perm_build_global_kernel<<<1, 32, 0, s>>>(p.dipiv, k0, (int)ns, (int)mrows, cx.idx_global, cx.src_top, cx.disp_dst, cx.disp_src, cx.disp_count);
   }
   count_launch();
-  B200_CUDA_TRY(cudaGetLastError());
+  return (int)cudaGetLastError();
+}
+// apply the permutation in cx's lists to columns [c0, c0 + ncols) of A
+template <typename T>
+int apply_perm(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t ns, int64_t c0, int64_t ncols, cudaStream_t s) {
+  if (ns <= 0 || ncols <= 0) return 0;
   T* A = (T*)p.A + k0;   // rows relative to k0
+  if (ns <= 256) {
+    const unsigned grid = (unsigned)std::min<int64_t>(ncols, (int64_t)cx.sms * 8);
+    perm_apply_fused_kernel<T><<<grid, 256, 0, s>>>((int)ns, ncols, cx.src_top, cx.disp_count, cx.disp_dst, cx.disp_src, A + c0 * p.lda, p.lda);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   const int64_t chunk = std::max<int64_t>(1, (int64_t)(cx.w_bytes / (sizeof(T) * (size_t)ns)));
   const unsigned gx = (unsigned)((ns + 255) / 256);
   for (int64_t c = 0; c < ncols; c += chunk) {
@@ -595,12 +1007,76 @@ int apply_pivots(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t 
   }
   return 0;
 }
+// apply the interchanges ipiv[k0 .. k0+ns) to columns [c0, c0 + ncols) of A (rows k0 .. m)
+template <typename T>
+int apply_pivots(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t ns, int64_t c0, int64_t ncols, cudaStream_t s) {
+  if (ns <= 0 || ncols <= 0) return 0;
+  B200_CUDA_TRY(build_perm(p, cx, k0, ns, s));
+  return apply_perm<T>(p, cx, k0, ns, c0, ncols, s);
+}
+
+// register-panel shapes per type: up to ROWS_WIDE rows the leaf is NBP_WIDE columns wide with RPT_WIDE rows per thread,
+// up to ROWS_TALL rows it is NBP_TALL x RPT_TALL (the register budget of 512 threads per CTA: 128 registers each)
+constexpr int REG_THREADS = 512, REG_MAXCL = 16;
+template <typename T> struct RegPanel {   // double, complex<float>: 8-byte scalars
+  static constexpr int NBP_WIDE = 32, RPT_WIDE = 1, NBP_TALL = 16, RPT_TALL = 2;
+  static constexpr int64_t ROWS_WIDE = (int64_t)REG_MAXCL * REG_THREADS * RPT_WIDE, ROWS_TALL = (int64_t)REG_MAXCL * REG_THREADS * RPT_TALL;
+};
+template <> struct RegPanel<float> {
+  static constexpr int NBP_WIDE = 32, RPT_WIDE = 1, NBP_TALL = 32, RPT_TALL = 2;
+  static constexpr int64_t ROWS_WIDE = (int64_t)REG_MAXCL * REG_THREADS * RPT_WIDE, ROWS_TALL = (int64_t)REG_MAXCL * REG_THREADS * RPT_TALL;
+};
+template <> struct RegPanel<double2> {
+  static constexpr int NBP_WIDE = 16, RPT_WIDE = 1, NBP_TALL = 8, RPT_TALL = 2;
+  static constexpr int64_t ROWS_WIDE = (int64_t)REG_MAXCL * REG_THREADS * RPT_WIDE, ROWS_TALL = (int64_t)REG_MAXCL * REG_THREADS * RPT_TALL;
+};
+// leaf width of the panel recursion for a panel of `mrows` rows
+template <typename T>
+int reg_leaf_width(int64_t mrows) {
+  static const int mode = [] { const char* e = getenv("B200BLAS_GETF2"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'c' ? 2 : 0)); }();
+  if (mode != 0 || mrows > RegPanel<T>::ROWS_TALL) return Leaf<T>::NB;
+  return mrows <= RegPanel<T>::ROWS_WIDE ? RegPanel<T>::NBP_WIDE : RegPanel<T>::NBP_TALL;
+}
+
+template <typename T, int NBP, int RPT>
+int launch_reg_panel(int64_t mrows, int nb, T* A, int64_t lda, int* ipiv, int64_t j0, int* info, cudaStream_t s) {
+  auto kern = getf2_reg_kernel<T, NBP, RPT, REG_THREADS>;
+  {
+    static std::atomic<uint64_t> done{0};
+    int dev = 0;
+    B200_CUDA_TRY(cudaGetDevice(&dev));
+    if (!((done.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull)) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      done.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
+    }
+  }
+  int cl = (int)((mrows + (int64_t)REG_THREADS * RPT - 1) / ((int64_t)REG_THREADS * RPT));
+  if (cl < 1) cl = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cl); cfg.blockDim = dim3(REG_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  B200_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, mrows, nb, A, lda, ipiv, j0, info, j0));
+  count_launch();
+  return 0;
+}
 
 template <typename T>
 int launch_panel(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t nc, cudaStream_t s) {
   constexpr int NBP = Leaf<T>::NB;
   const int64_t mrows = p.m - j0;
-  static const bool use_cluster = [] { const char* e = getenv("B200BLAS_GETF2"); return e && e[0] == 'c'; }();   // DRAFT, opt-in
+  // B200BLAS_GETF2: "reg" (default) register-resident cluster panel; "slab" round 1's cooperative shared-memory slab kernel;
+  // "cluster" the slab kernel on one cluster (forced variants for the sweeps)
+  static const int mode = [] { const char* e = getenv("B200BLAS_GETF2"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'c' ? 2 : 0)); }();
+  if (mode == 0 && mrows <= RegPanel<T>::ROWS_TALL && nc <= reg_leaf_width<T>(mrows)) {
+    T* Ap = (T*)p.A + j0 + j0 * p.lda;
+    if (mrows <= RegPanel<T>::ROWS_WIDE)
+      return launch_reg_panel<T, RegPanel<T>::NBP_WIDE, RegPanel<T>::RPT_WIDE>(mrows, (int)nc, Ap, p.lda, p.dipiv + j0, j0, p.dinfo, s);
+    return launch_reg_panel<T, RegPanel<T>::NBP_TALL, RegPanel<T>::RPT_TALL>(mrows, (int)nc, Ap, p.lda, p.dipiv + j0, j0, p.dinfo, s);
+  }
+  const bool use_cluster = mode == 2;
   if (use_cluster) {
     constexpr int MAXCL = 16;
     int cl = (int)std::min<int64_t>(MAXCL, (mrows + 255) / 256);
@@ -651,7 +1127,7 @@ int launch_panel(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t 
 // factor columns [j0, j0 + nc) over rows [j0, m); requires j0 + nc <= min(m, n)
 template <typename T>
 int getrf_rec(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t nc, cudaStream_t s) {
-  constexpr int NBP = Leaf<T>::NB;
+  const int NBP = reg_leaf_width<T>(p.m - j0);
   if (nc <= NBP) return launch_panel<T>(p, cx, j0, nc, s);
   const int64_t n1 = split_point(nc, NBP), n2 = nc - n1;
   T* A = (T*)p.A;
@@ -676,6 +1152,98 @@ int getrf_rec(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t nc,
   return apply_pivots<T>(p, cx, j0 + n1, n2, j0, n1, s);                 // interchanges of the right half -> left half
 }
 
+// B := inv(L11) * B for the unit-lower jb x jb block at the top of panel j0, B = jb x ncols at column c0: one product on the
+// tensor-pipe kernels against the block's inverse (Vinv, from launch_trtri_diag) plus a copy back, or -- B200BLAS_TRSM=subst --
+// the substitution leaf (PartialPivLU.h:490)
+template <typename T>
+int panel_row_solve(const GetrfProblem& p, int64_t j0, int64_t jb, int64_t c0, int64_t ncols, const void* Vinv, void* Xtmp, cudaStream_t s) {
+  if (ncols <= 0) return 0;
+  T* A = (T*)p.A;
+  TriProblem t;
+  t.type = p.type; t.left = 1; t.uplo = UPLO_LOWER; t.op = OP_N; t.unit = 1; t.m = jb; t.n = ncols;
+  t.alpha[0] = 1.0; t.alpha[1] = 0.0;
+  t.A = A + j0 + j0 * p.lda; t.lda = p.lda; t.B = A + j0 + c0 * p.lda; t.ldb = p.lda;
+  if (!trsm_substitution_forced()) { t.Vinv = Vinv; t.Xtmp = Xtmp; }
+  return launch_trsm(t, s);
+}
+// A[r0.., c0..c0+ncols) -= A[r0.., j0..j0+jb) * A[j0..j0+jb, c0..c0+ncols)   (PartialPivLU.h:492)
+template <typename T>
+int panel_trailing_update(const GetrfProblem& p, int64_t j0, int64_t jb, int64_t c0, int64_t ncols, cudaStream_t s) {
+  const int64_t r0 = j0 + jb, mlow = p.m - r0;
+  if (mlow <= 0 || ncols <= 0) return 0;
+  T* A = (T*)p.A;
+  GemmProblem g;
+  g.type = p.type; g.opa = OP_N; g.opb = OP_N; g.m = mlow; g.n = ncols; g.k = jb;
+  g.alpha[0] = -1.0; g.alpha[1] = 0.0; g.beta[0] = 1.0; g.beta[1] = 0.0;
+  g.A = A + r0 + j0 * p.lda; g.lda = p.lda;
+  g.B = A + j0 + c0 * p.lda; g.ldb = p.lda;
+  g.C = A + r0 + c0 * p.lda; g.ldc = p.lda;
+  return run_gemm_device(g, s, B200BLAS_AUTO);
+}
+
+// Right-looking blocked LU with one step of look-ahead -- the blocked loop of PartialPivLU.h:426-496 with blockSize = NBO:
+//   panel chain (stream sp): factor the panel (recursion over register-resident leaves) -> invert its L11 -> interchanges,
+//                            row solve and update of the NEXT block column only -> factor the next panel ...
+//   bulk (the caller's stream): interchanges left of the panel and right of the next block column, row solve and the large
+//                            update A22 -= A21 A12 there,
+// so that the latency-bound panel of step j+1 runs underneath the tensor-pipe update of step j.  cx / cx2 hold the
+// permutation lists of the two streams.
+template <typename T>
+int getrf_blocked(const GetrfProblem& p, const GetrfCtx& cx, const GetrfCtx& cx2, void* Vinv0, void* Vinv1, void* Xtmp, void* Xtmp2, cudaStream_t s) {
+  const int NBO = trsm_leaf_order(p.type);   // 128 (64 for complex double): one inverse block per panel
+  const int64_t size = std::min(p.m, p.n);
+  const bool look = lookahead_enabled() && size > 4 * NBO;
+  cudaStream_t sp = s;
+  LookAhead& la = t_look;
+  if (look) {
+    B200_CUDA_TRY(la.init());
+    sp = la.sp;
+    B200_CUDA_TRY(cudaEventRecord(la.e_in, s));
+    B200_CUDA_TRY(cudaStreamWaitEvent(sp, la.e_in, 0));
+  }
+  bool rest_pending = false;
+  for (int64_t j = 0; j < size; j += NBO) {
+    const int64_t jb = std::min<int64_t>(NBO, size - j), r1 = j + jb;
+    const int64_t nb2 = r1 < size ? std::min<int64_t>(NBO, size - r1) : 0;   // width of the next panel
+    const int64_t c_rest = r1 + nb2, n_rest = p.n - c_rest;
+    B200_CUDA_TRY(getrf_rec<T>(p, cx, j, jb, sp));
+    // two inverse buffers, alternating: the bulk update of step j may still read its inverse while the panel chain of
+    // step j+1 writes the next one (the chain only passes step j+1 after the bulk update of step j, see e_rest)
+    void* Vinv = ((j / NBO) & 1) ? Vinv1 : Vinv0;
+    const bool have_right = p.n > r1;
+    if (have_right) {
+      TriProblem t;
+      t.type = p.type; t.left = 1; t.uplo = UPLO_LOWER; t.op = OP_N; t.unit = 1; t.m = jb; t.n = 1;
+      t.A = (T*)p.A + j + j * p.lda; t.lda = p.lda;
+      if (!trsm_substitution_forced()) B200_CUDA_TRY(launch_trtri_diag(t, Vinv, sp));
+    }
+    if (look) B200_CUDA_TRY(cudaEventRecord(la.e_panel, sp));
+    if (nb2 > 0) {   // next block column on the panel stream
+      if (look && rest_pending) B200_CUDA_TRY(cudaStreamWaitEvent(sp, la.e_rest, 0));   // the previous bulk update wrote these columns
+      B200_CUDA_TRY(build_perm(p, cx, j, jb, sp));
+      B200_CUDA_TRY(apply_perm<T>(p, cx, j, jb, r1, nb2, sp));
+      B200_CUDA_TRY(panel_row_solve<T>(p, j, jb, r1, nb2, Vinv, Xtmp, sp));
+      B200_CUDA_TRY(panel_trailing_update<T>(p, j, jb, r1, nb2, sp));
+    }
+    if (j > 0 || n_rest > 0) {   // bulk: columns left of the panel and right of the next block column
+      if (look) B200_CUDA_TRY(cudaStreamWaitEvent(s, la.e_panel, 0));
+      B200_CUDA_TRY(build_perm(p, cx2, j, jb, s));
+      B200_CUDA_TRY(apply_perm<T>(p, cx2, j, jb, 0, j, s));
+      if (n_rest > 0) {
+        B200_CUDA_TRY(apply_perm<T>(p, cx2, j, jb, c_rest, n_rest, s));
+        B200_CUDA_TRY(panel_row_solve<T>(p, j, jb, c_rest, n_rest, Vinv, Xtmp2, s));
+        B200_CUDA_TRY(panel_trailing_update<T>(p, j, jb, c_rest, n_rest, s));
+      }
+      if (look) { B200_CUDA_TRY(cudaEventRecord(la.e_rest, s)); rest_pending = true; }
+    }
+  }
+  if (look) {
+    B200_CUDA_TRY(cudaEventRecord(la.e_out, sp));
+    B200_CUDA_TRY(cudaStreamWaitEvent(s, la.e_out, 0));
+  }
+  return 0;
+}
+
 template <typename T>
 int getrf_typed(const GetrfProblem& p, cudaStream_t s) {
   GetrfCtx cx;
@@ -687,8 +1255,11 @@ int getrf_typed(const GetrfProblem& p, cudaStream_t s) {
   cx.max_dyn_smem = (size_t)optin;
   B200_SET_MAX_DYN_SMEM_ONCE(perm_build_kernel, optin - 1024);
   const int64_t size = std::min(p.m, p.n);
-  // workspace: permutation lists (4 * size ints + m ints for the slow path), panel scratch, gather buffer
-  const size_t ints = (size_t)size * 3 + 16 + (size_t)p.m;
+  // default: right-looking blocked loop with look-ahead; B200BLAS_GETRF=rec keeps round 1's full recursion (forced variant)
+  static const bool recursive = [] { const char* e = getenv("B200BLAS_GETRF"); return e && e[0] == 'r'; }();
+  // workspace: two sets of permutation lists (3 * size + 16 ints, + m ints for the slow path; one set per stream), panel
+  // scratch, gather buffer, the inverse of a panel's L11 and two scratch panels for the row solves
+  const size_t ints_one = ((size_t)size * 3 + 16 + (size_t)p.m + 63) / 64 * 64;
   const size_t ps = panel_scratch_bytes<T>(cx.sms);
   cx.w_bytes = std::min<size_t>((size_t)64 << 20, std::max<size_t>((size_t)1 << 20, (size_t)size * (size_t)p.n * sizeof(T)));
   // a gather chunk must hold at least one column of `size / 2` rows
@@ -699,23 +1270,39 @@ int getrf_typed(const GetrfProblem& p, cudaStream_t s) {
   const int64_t rpc0 = (p.m + gmax - 1) / gmax;
   size_t gslab_bytes = 0;
   if ((size_t)rpc0 * (NBP + 1) * sizeof(T) + 4096 > cx.max_dyn_smem) gslab_bytes = (size_t)gmax * (size_t)rpc0 * (NBP + 1) * sizeof(T);
-  const size_t total = (ints * sizeof(int) + 255) / 256 * 256 + (ps + 255) / 256 * 256 + (cx.w_bytes + 255) / 256 * 256 + gslab_bytes;
+  const size_t lb = (size_t)trsm_leaf_order(p.type);
+  const size_t vinv_bytes = recursive ? 0 : (lb * lb * sizeof(T) + 255) / 256 * 256;
+  const size_t xtmp_bytes = recursive ? 0 : (lb * (size_t)p.n * sizeof(T) + 255) / 256 * 256;
+  const size_t total = 2 * ints_one * sizeof(int) + (ps + 255) / 256 * 256 + (cx.w_bytes + 255) / 256 * 256 + (gslab_bytes + 255) / 256 * 256 +
+                       2 * vinv_bytes + 2 * xtmp_bytes;
   unsigned char* ws = nullptr;
   B200_CUDA_TRY(cudaMallocAsync((void**)&ws, total, s));
-  int* ip = (int*)ws;
-  cx.src_top = ip; cx.disp_dst = ip + size; cx.disp_src = ip + 2 * size; cx.disp_count = ip + 3 * size; cx.idx_global = ip + 3 * size + 16;
-  cx.panel_scratch = ws + (ints * sizeof(int) + 255) / 256 * 256;
+  auto lists = [&](GetrfCtx& c, int* ip) {
+    c.src_top = ip; c.disp_dst = ip + size; c.disp_src = ip + 2 * size; c.disp_count = ip + 3 * size; c.idx_global = ip + 3 * size + 16;
+  };
+  lists(cx, (int*)ws);
+  cx.panel_scratch = ws + 2 * ints_one * sizeof(int);
   cx.W = cx.panel_scratch + (ps + 255) / 256 * 256;
-  if (gslab_bytes) cx.gslab = (unsigned char*)cx.W + (cx.w_bytes + 255) / 256 * 256;
-  int e = getrf_rec<T>(p, cx, 0, size, s);
-  if (!e && p.n > size) {   // wide matrix: the columns right of the square part (LAPACK semantics)
-    e = apply_pivots<T>(p, cx, 0, size, size, p.n - size, s);
-    if (!e) {
-      TriProblem t;
-      t.type = p.type; t.left = 1; t.uplo = UPLO_LOWER; t.op = OP_N; t.unit = 1; t.m = size; t.n = p.n - size;
-      t.alpha[0] = 1.0; t.alpha[1] = 0.0;
-      t.A = p.A; t.lda = p.lda; t.B = (T*)p.A + size * p.lda; t.ldb = p.lda;
-      e = launch_trsm(t, s);
+  unsigned char* after_w = (unsigned char*)cx.W + (cx.w_bytes + 255) / 256 * 256;
+  if (gslab_bytes) cx.gslab = after_w;
+  unsigned char* vinv = after_w + (gslab_bytes + 255) / 256 * 256;
+  GetrfCtx cx2 = cx;   // the bulk stream's permutation lists (interchanges of <= 256 rows never use W)
+  lists(cx2, (int*)ws + ints_one);
+  int e;
+  if (!recursive) {
+    e = getrf_blocked<T>(p, cx, cx2, vinv, vinv + vinv_bytes, vinv + 2 * vinv_bytes, vinv + 2 * vinv_bytes + xtmp_bytes, s);
+    if (e) cudaDeviceSynchronize();   // the panel stream may still be using the workspace
+  } else {
+    e = getrf_rec<T>(p, cx, 0, size, s);
+    if (!e && p.n > size) {   // wide matrix: the columns right of the square part (LAPACK semantics)
+      e = apply_pivots<T>(p, cx, 0, size, size, p.n - size, s);
+      if (!e) {
+        TriProblem t;
+        t.type = p.type; t.left = 1; t.uplo = UPLO_LOWER; t.op = OP_N; t.unit = 1; t.m = size; t.n = p.n - size;
+        t.alpha[0] = 1.0; t.alpha[1] = 0.0;
+        t.A = p.A; t.lda = p.lda; t.B = (T*)p.A + size * p.lda; t.ldb = p.lda;
+        e = launch_trsm(t, s);
+      }
     }
   }
   cudaFreeAsync(ws, s);
@@ -727,6 +1314,17 @@ int getrf_typed(const GetrfProblem& p, cudaStream_t s) {
 // *p.dinfo must hold INT_MAX on entry; on exit it is the smallest failing 1-based index, or still INT_MAX
 int launch_potrf(const PotrfProblem& p, cudaStream_t s) {
   if (p.n <= 0) return 0;
+  // default: right-looking blocked loop with look-ahead; B200BLAS_POTRF=rec keeps round 1's recursion (forced variant for the sweeps)
+  static const bool recursive = [] { const char* e = getenv("B200BLAS_POTRF"); return e && e[0] == 'r'; }();
+  if (!recursive) {
+    note_variant("potrf_blocked_lookahead_cta128+leaf+syrk");
+    switch (p.type) {
+      case TY_S: return potrf_blocked<float>(p, s);
+      case TY_D: return potrf_blocked<double>(p, s);
+      case TY_C: return potrf_blocked<float2>(p, s);
+      default: return potrf_blocked<double2>(p, s);
+    }
+  }
   note_variant("potrf_recursive_leaf+trsm+syrk");
   switch (p.type) {
     case TY_S: return potrf_rec<float>(p, 0, p.n, s);
@@ -738,7 +1336,7 @@ int launch_potrf(const PotrfProblem& p, cudaStream_t s) {
 
 int launch_getrf(const GetrfProblem& p, cudaStream_t s) {
   if (p.m <= 0 || p.n <= 0) return 0;
-  note_variant("getrf_recursive_panel+trsm+gemm");
+  note_variant("getrf_blocked_lookahead_regpanel+inv+gemm");
   switch (p.type) {
     case TY_S: return getrf_typed<float>(p, s);
     case TY_D: return getrf_typed<double>(p, s);

@@ -399,10 +399,17 @@ int run_tri(const TriProblem& p, cudaStream_t s) {
   const bool zero = p.alpha[0] == 0.0 && p.alpha[1] == 0.0;
   if (!zero) {   // alpha == 0: the result is zero whatever A holds (netlib ?TRSM/?TRMM quick path)
     const bool t_lower = (p.uplo == UPLO_LOWER) == (p.op == OP_N);
-    static const bool use_inv = [] { const char* e = getenv("B200BLAS_TRSM"); return e && e[0] == 'i'; }();   // DRAFT, opt-in
-    if (SOLVE && use_inv) {
-      constexpr int LB = LeafOrder<T>::NB * LeafOrder<T>::NSUB;
-      const int64_t na = p.left ? p.m : p.n, nrhs = p.left ? p.n : p.m;
+    // leaves: B200BLAS_TRSM=inv forces the inverse-based leaves (one batched inversion of all diagonal blocks, then every
+    // leaf is a product on the tensor-pipe kernels), =subst the substitution leaf; default: inverse leaves for large solves
+    // (measured on B200, profiles/bench_r02: dtrsm 8192 21.9 -> 28.3 TFLOP/s), substitution where the inversion of the
+    // whole triangle would not be amortised (the panel solves inside ?potrf_ / ?getrf_)
+    static const int leaf_env = [] { const char* e = getenv("B200BLAS_TRSM"); return !e ? 0 : (e[0] == 'i' ? 1 : (e[0] == 's' ? 2 : 0)); }();
+    constexpr int LB = LeafOrder<T>::NB * LeafOrder<T>::NSUB;
+    const int64_t na = p.left ? p.m : p.n, nrhs = p.left ? p.n : p.m;
+    const bool use_inv = leaf_env == 1 || (leaf_env == 0 && na >= 2048 && nrhs >= 1024);
+    if (SOLVE && p.Vinv && p.Xtmp) {   // the caller (lapack.cu) already holds the inverses of the diagonal blocks
+      B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, 0, na, s)));
+    } else if (SOLVE && use_inv) {
       const int64_t nblocks = (na + LB - 1) / LB;
       const size_t vbytes = (size_t)nblocks * LB * LB * sizeof(T), xbytes = (size_t)LB * (size_t)nrhs * sizeof(T);
       unsigned char* ws = nullptr;
@@ -448,6 +455,35 @@ int expand_typed(const SymmProblem& p, int64_t na, void* W, int64_t ldw, cudaStr
 }  // namespace
 
 int launch_trsm(const TriProblem& p, cudaStream_t s) { return dispatch_tri<true>(p, s); }
+
+// inverses of the diagonal leaf blocks of op(A) (order trsm_leaf_order(type) each, stored densely one after the other in V):
+// what TriProblem::Vinv expects.  Lets ?getrf_ invert a panel's L11 once and use it for several solves on different streams.
+int trsm_leaf_order(int type) {
+  return type == TY_Z ? LeafOrder<double2>::NB * LeafOrder<double2>::NSUB : LeafOrder<double>::NB * LeafOrder<double>::NSUB;
+}
+template <typename T>
+static int trtri_typed(const TriProblem& p, void* V, cudaStream_t s) {
+  constexpr int LB = LeafOrder<T>::NB * LeafOrder<T>::NSUB;
+  const bool t_lower = (p.uplo == UPLO_LOWER) == (p.op == OP_N);
+  const int64_t na = p.left ? p.m : p.n;
+  constexpr size_t smem = 5 * (size_t)(LB / 2) * (LB / 2) * sizeof(T);
+  B200_SET_MAX_DYN_SMEM_ONCE((trtri_diag_kernel<T, LB>), smem);
+  trtri_diag_kernel<T, LB><<<(unsigned)((na + LB - 1) / LB), 256, smem, s>>>(p.op, p.uplo, p.unit, t_lower ? 1 : 0, na, (const T*)p.A, p.lda, (T*)V);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+int launch_trtri_diag(const TriProblem& p, void* V, cudaStream_t s) {
+  switch (p.type) {
+    case TY_S: return trtri_typed<float>(p, V, s);
+    case TY_D: return trtri_typed<double>(p, V, s);
+    case TY_C: return trtri_typed<float2>(p, V, s);
+    default: return trtri_typed<double2>(p, V, s);
+  }
+}
+bool trsm_substitution_forced() {
+  static const bool v = [] { const char* e = getenv("B200BLAS_TRSM"); return e && e[0] == 's'; }();
+  return v;
+}
 int launch_trmm(const TriProblem& p, cudaStream_t s) { return dispatch_tri<false>(p, s); }
 
 size_t symm_workspace_bytes(const SymmProblem& p) {

@@ -49,6 +49,23 @@ def test_getrf_sweep_and_pivots_match_the_oracle(L, t):
             assert np.abs(a[:m] - b[:m]).max(initial=0.0) <= 4096 * oa.EPS[t] * max(1.0, float(np.abs(b[:m]).max(initial=0.0)))
 
 
+@pytest.mark.parametrize("t,m,n", [("d", 9000, 70), ("s", 9000, 70), ("z", 9000, 40), ("d", 16384, 33), ("c", 20000, 48), ("d", 140000, 40),
+                                   ("z", 70000, 20)])
+def test_getrf_tall_panels(L, t, m, n):
+    """Panel heights on both sides of every leaf-kernel boundary (lapack.cu RegPanel: <= 8192 rows wide register leaf, <= 16384
+    narrow one with two rows per thread, above that the cooperative slab kernel, and past ~120k rows of doubles its
+    global-memory slab -- ADVICE r1: a 200000 x 64 LU must not fail); pivots identical to the oracle port's."""
+    rng = np.random.default_rng(14)
+    a0 = oa.rand_matrix(rng, t, m, n, ld=m + 1)
+    a = a0.copy(order="F")
+    ipiv, info = oa.call_getrf(getattr(L, t + "getrf_"), m, n, a, m + 1)
+    lp.check_getrf(t, m, n, a0, a, ipiv, info)
+    b = a0.copy(order="F")
+    opiv, oinfo = oa.call_getrf(getattr(P, "oracle_%sgetrf_" % t), m, n, b, m + 1)
+    assert oinfo == info
+    assert np.array_equal(opiv, ipiv), (t, m, n)
+
+
 @pytest.mark.parametrize("t", list("sdcz"))
 def test_failure_reports(L, t):
     rng = np.random.default_rng(6)
