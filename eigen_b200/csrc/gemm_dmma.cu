@@ -176,13 +176,27 @@ __device__ __forceinline__ void tile_of(int64_t pid, int64_t tiles_m, int64_t ti
   tn = in / gsz;
 }
 
+// inverse of tile_of: position of tile (tm, tn) in the launch order
+__device__ __forceinline__ int64_t pid_of(int64_t tm, int64_t tn, int64_t tiles_m, int64_t tiles_n) {
+  const int64_t g = tm / GROUP, first = g * GROUP;
+  const int64_t gsz = (tiles_m - first < GROUP) ? (tiles_m - first) : GROUP;
+  return g * GROUP * tiles_n + tn * gsz + (tm - first);
+}
+// Wave-quantisation tail: the main launch covers the first `covered` tiles of the big-tile grid (a whole number of waves),
+// a second launch with the small tile covers the rest and skips everything the main launch owns.
+struct TailSkip {
+  int64_t covered = 0;                   // 0: ordinary launch
+  int64_t big_tiles_m = 0, big_tiles_n = 0;
+  int ratio_m = 1, ratio_n = 1;          // small tiles per big tile along m / n
+};
+
 // TRI: the triangular mask of ?syrk_/?herk_/?syr2k_/?her2k_ is compiled in.  The plain product is a separate
 // instantiation without a single mask instruction: with the mask tests in the epilogue the 16384^3 dgemm ran 1.8 %
 // slower (A/B on the same B200: 257.0 -> 261.8 ms), although the mask is never active there.
 template <typename C, bool CPLX, int AMODE, int BMODE, bool TRI>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double* __restrict__ Cmat, int64_t ldc,
-                 EpiParams ep, int64_t tiles_m, int64_t tiles_n) {
+                 EpiParams ep, int64_t tiles_m, int64_t tiles_n, TailSkip skip) {
   extern __shared__ __align__(16) double smem[];
   double* As = smem;
   double* Bs = smem + C::STAGES * C::PANEL_A;
@@ -192,6 +206,8 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
   const int wm = warp % C::WARPS_M, wn = warp / C::WARPS_M;
   int64_t tm, tn;
   tile_of(blockIdx.x, tiles_m, tiles_n, tm, tn);
+  // tail launch (launch_split_tail): tiles already covered by the first `covered` big tiles of the main launch are not ours
+  if (skip.covered > 0 && pid_of(tm / skip.ratio_m, tn / skip.ratio_n, skip.big_tiles_m, skip.big_tiles_n) < skip.covered) return;
   constexpr int SC = CPLX ? 2 : 1;  // real rows/cols per scalar
   const int64_t m0 = tm * (C::BM / SC), n0 = tn * (C::BN / SC);  // tile origin in scalars
   if constexpr (TRI) {
@@ -433,46 +449,52 @@ using CfgM = Cfg<128, 64, 32, 32, 2, 16, 4, true>;   // same tile, mbarrier pipe
 // many SMs finishes the same product up to 4x sooner.
 using CfgS = Cfg<64, 32, 16, 16, 3, 16, 4, true>;
 
+// grid_limit > 0: only the first grid_limit tiles of the launch order (the main part of a split launch)
 template <typename C, bool CPLX, int AMODE, int BMODE>
-int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
+int launch_cfg(const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep,
+               int64_t grid_limit = 0, const TailSkip& skip = TailSkip()) {
   const int sc = CPLX ? 2 : 1;
   const int64_t tiles_m = (p.m * sc + C::BM - 1) / C::BM, tiles_n = (p.n * sc + C::BN - 1) / C::BN;
-  const int64_t tiles = tiles_m * tiles_n;
+  int64_t tiles = tiles_m * tiles_n;
   if (tiles > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+  if (grid_limit > 0 && grid_limit < tiles) tiles = grid_limit;
   if (p.uplo != UPLO_FULL) {
     B200_SET_MAX_DYN_SMEM_ONCE((dmma_gemm_kernel<C, CPLX, AMODE, BMODE, true>), C::SMEM_BYTES);
     dmma_gemm_kernel<C, CPLX, AMODE, BMODE, true><<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(
-        a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep, tiles_m, tiles_n);
+        a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep, tiles_m, tiles_n, skip);
   } else {
     B200_SET_MAX_DYN_SMEM_ONCE((dmma_gemm_kernel<C, CPLX, AMODE, BMODE, false>), C::SMEM_BYTES);
     dmma_gemm_kernel<C, CPLX, AMODE, BMODE, false><<<(unsigned)tiles, C::THREADS, C::SMEM_BYTES, s>>>(
-        a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep, tiles_m, tiles_n);
+        a, b, p.m, p.n, p.k, (double*)p.C, p.ldc, ep, tiles_m, tiles_n, skip);
   }
   count_launch();
   return (int)cudaGetLastError();
 }
 
 template <typename CF, bool CPLX, int AMODE>
-int launch_b(int bmode, const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep) {
+int launch_b(int bmode, const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b, const EpiParams& ep,
+             int64_t grid_limit, const TailSkip& skip) {
   if constexpr (CPLX) {
-    return bmode == LD_K ? launch_cfg<CF, true, AMODE, LD_K>(p, s, a, b, ep) : launch_cfg<CF, true, AMODE, LD_DIM16>(p, s, a, b, ep);
+    return bmode == LD_K ? launch_cfg<CF, true, AMODE, LD_K>(p, s, a, b, ep, grid_limit, skip)
+                         : launch_cfg<CF, true, AMODE, LD_DIM16>(p, s, a, b, ep, grid_limit, skip);
   } else {
     switch (bmode) {
-      case LD_DIM16: return launch_cfg<CF, false, AMODE, LD_DIM16>(p, s, a, b, ep);
-      case LD_DIM8: return launch_cfg<CF, false, AMODE, LD_DIM8>(p, s, a, b, ep);
-      default: return launch_cfg<CF, false, AMODE, LD_K>(p, s, a, b, ep);
+      case LD_DIM16: return launch_cfg<CF, false, AMODE, LD_DIM16>(p, s, a, b, ep, grid_limit, skip);
+      case LD_DIM8: return launch_cfg<CF, false, AMODE, LD_DIM8>(p, s, a, b, ep, grid_limit, skip);
+      default: return launch_cfg<CF, false, AMODE, LD_K>(p, s, a, b, ep, grid_limit, skip);
     }
   }
 }
 
 template <typename CF>
 int launch_modes(bool cplx, int amode, int bmode, const GemmProblem& p, cudaStream_t s, const PanelSrc& a, const PanelSrc& b,
-                 const EpiParams& ep) {
-  if (cplx) return amode == LD_K ? launch_b<CF, true, LD_K>(bmode, p, s, a, b, ep) : launch_b<CF, true, LD_DIM16>(bmode, p, s, a, b, ep);
+                 const EpiParams& ep, int64_t grid_limit = 0, const TailSkip& skip = TailSkip()) {
+  if (cplx) return amode == LD_K ? launch_b<CF, true, LD_K>(bmode, p, s, a, b, ep, grid_limit, skip)
+                                 : launch_b<CF, true, LD_DIM16>(bmode, p, s, a, b, ep, grid_limit, skip);
   switch (amode) {
-    case LD_DIM16: return launch_b<CF, false, LD_DIM16>(bmode, p, s, a, b, ep);
-    case LD_DIM8: return launch_b<CF, false, LD_DIM8>(bmode, p, s, a, b, ep);
-    default: return launch_b<CF, false, LD_K>(bmode, p, s, a, b, ep);
+    case LD_DIM16: return launch_b<CF, false, LD_DIM16>(bmode, p, s, a, b, ep, grid_limit, skip);
+    case LD_DIM8: return launch_b<CF, false, LD_DIM8>(bmode, p, s, a, b, ep, grid_limit, skip);
+    default: return launch_b<CF, false, LD_K>(bmode, p, s, a, b, ep, grid_limit, skip);
   }
 }
 
@@ -536,12 +558,34 @@ int launch_dmma(const GemmProblem& p, cudaStream_t s) {
     int rc;
     static const int tile_env = [] { const char* e = getenv("B200BLAS_DMMA_TILE"); return !e ? 0 : (e[0] == 's' ? 1 : 2); }();
     const int64_t big_tiles = ((q.m * sc + CfgM::BM - 1) / CfgM::BM) * ((q.n * sc + CfgM::BN - 1) / CfgM::BN);
-    if (tile_env == 1 || (tile_env == 0 && big_tiles <= 100)) {
+    // up to 222 big tiles (three quarters of one wave of 296) the quarter-size tile finishes sooner: 4r small tiles are at
+    // most two waves of ~3/8 the duration each (measured round 1: 1024^3 23.6 vs 22.9 TF, 1536^3 = 288 tiles 29.4 vs 30.3)
+    if (tile_env == 1 || (tile_env == 0 && big_tiles <= 222)) {
       note_variant(cplx ? "dmma_z_32x16x16_w8x8_3cta_mbar" : "dmma_d_64x32x16_w16x16_3cta_mbar");
       rc = launch_modes<CfgS>(cplx, amode, bmode, q, s, a2, b2, e2);
     } else if (use_mbar()) {
-      note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta_mbar" : "dmma_d_128x64x16_w32x32_2cta_mbar");
-      rc = launch_modes<CfgM>(cplx, amode, bmode, q, s, a2, b2, e2);
+      // Wave quantisation: the big tile runs 2 CTAs per SM = `slots` tiles per wave.  When the last wave would be at most
+      // three quarters full, the main launch stops at a whole number of waves and the rest runs on the quarter-size tile
+      // (3 CTAs per SM): r big tiles = 4r small ones = ceil(4r / (3 * SMs)) waves of ~3/8 the duration.  2048^3: 512 tiles
+      // = 1.73 waves -> 1 + 2 * 0.375 instead of 2 (B200BLAS_DMMA_TAIL=0 disables).
+      static const bool tail_on = [] { const char* e = getenv("B200BLAS_DMMA_TAIL"); return !(e && e[0] == '0'); }();
+      static const int sms = [] { int d = 0, n = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+      const int64_t slots = 2 * (int64_t)sms, waves = big_tiles / slots, rest = big_tiles - waves * slots;
+      const int64_t small_waves = (4 * rest + 3 * sms - 1) / (3 * sms);
+      if (tail_on && q.uplo == UPLO_FULL && rest > 0 && waves >= 1 && waves <= 24 && 3 * small_waves < 8) {
+        note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta_mbar+tail" : "dmma_d_128x64x16_w32x32_2cta_mbar+tail");
+        rc = launch_modes<CfgM>(cplx, amode, bmode, q, s, a2, b2, e2, waves * slots);
+        if (!rc) {
+          TailSkip sk;
+          sk.covered = waves * slots;
+          sk.big_tiles_m = (q.m * sc + CfgM::BM - 1) / CfgM::BM; sk.big_tiles_n = (q.n * sc + CfgM::BN - 1) / CfgM::BN;
+          sk.ratio_m = CfgM::BM / CfgS::BM; sk.ratio_n = CfgM::BN / CfgS::BN;
+          rc = launch_modes<CfgS>(cplx, amode, bmode, q, s, a2, b2, e2, 0, sk);
+        }
+      } else {
+        note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta_mbar" : "dmma_d_128x64x16_w32x32_2cta_mbar");
+        rc = launch_modes<CfgM>(cplx, amode, bmode, q, s, a2, b2, e2);
+      }
     } else {
       note_variant(cplx ? "dmma_z_64x32x16_w16x16_2cta" : "dmma_d_128x64x16_w32x32_2cta");
       rc = launch_modes<CfgB>(cplx, amode, bmode, q, s, a2, b2, e2);

@@ -100,6 +100,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// hi = tf32(x) (round to nearest), lo = tf32(x - hi).  Non-finite values must behave as in the reference's fp32 FMA path:
+// x = +-Inf would give lo = Inf - Inf = NaN, and a finite |x| just below FLT_MAX rounds UP to Inf under cvt.rna -- the
+// first keeps lo = 0 (Inf propagates through hi alone), the second truncates instead of rounding so that hi stays finite.
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  if ((h & 0x7f800000u) == 0x7f800000u) {
+    const uint32_t xb = __float_as_uint(x);
+    if ((xb & 0x7f800000u) != 0x7f800000u) h = xb & 0xffffe000u;
+  }
+  float res = x - __uint_as_float(h);
+  if ((h & 0x7f800000u) == 0x7f800000u) res = 0.f;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
+  hi = __uint_as_float(h);
+  lo = __uint_as_float(l);
+}
+
 // ---------------- pack: split op(X) into K-major tf32 hi / lo panels -----------------------------------------
 // element (r, kk) of the logical R x K operand lives at src[r*sr + kk*sk]; exactly one of sr, sk is 1.
 __global__ void __launch_bounds__(256)
@@ -126,13 +143,10 @@ tf32_split_pack_kernel(const float* __restrict__ src, int64_t sr, int64_t sk, in
   for (int j = ty; j < 32; j += 8) {
     const int64_t r = r0 + j, kk = k0 + tx;
     if (r < R && kk < Kp) {
-      const float x = t[j][tx];
-      uint32_t h, l;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-      const float res = x - __uint_as_float(h);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
-      hi[r * Kp + kk] = __uint_as_float(h);
-      lo[r * Kp + kk] = __uint_as_float(l);
+      float h, l;
+      tf32_split(t[j][tx], h, l);
+      hi[r * Kp + kk] = h;
+      lo[r * Kp + kk] = l;
     }
   }
 }
@@ -713,17 +727,13 @@ tf32_split_pack_cplx_kernel(const float2* __restrict__ src, int64_t sr, int64_t 
     if (r < R && kk < Kp) {
       float2 x = t[j][tx];
       if (conj) x.y = -x.y;
-      uint32_t h, l;
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x.x));
-      float res = x.x - __uint_as_float(h);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
-      re_hi[r * Kp + kk] = __uint_as_float(h);
-      re_lo[r * Kp + kk] = __uint_as_float(l);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x.y));
-      res = x.y - __uint_as_float(h);
-      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(res));
-      im_hi[r * Kp + kk] = __uint_as_float(h);
-      im_lo[r * Kp + kk] = __uint_as_float(l);
+      float h, l;
+      tf32_split(x.x, h, l);
+      re_hi[r * Kp + kk] = h;
+      re_lo[r * Kp + kk] = l;
+      tf32_split(x.y, h, l);
+      im_hi[r * Kp + kk] = h;
+      im_lo[r * Kp + kk] = l;
     }
   }
 }

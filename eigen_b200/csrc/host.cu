@@ -223,7 +223,8 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
     B200_CUDA_TRY(cudaEventRecord(st.ev_ac[c], st.s_in));
     return 0;
   };
-  for (int j = 0; j < nslabs; ++j) {
+  // inputs of column slab j: the slab of op(B) and (beta != 0) of C
+  auto upload_slab_inputs = [&](int j) -> int {
     const int64_t j0 = (int64_t)j * slab, nj = std::min<int64_t>(slab, n - j0);
     if (have_product) {
       if (opb == OP_N) {
@@ -241,32 +242,22 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
       t_h2d += (uint64_t)m * nj * es;
     }
     B200_CUDA_TRY(cudaEventRecord(st.ev_in[j], st.s_in));
-    B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_in[j], 0));
+    return (int)cudaStreamWaitEvent(st.s_comp, st.ev_in[j], 0);
+  };
+  auto slab_problem = [&](int j) {
+    const int64_t j0 = (int64_t)j * slab, nj = std::min<int64_t>(slab, n - j0);
     GemmProblem p;
     p.type = type; p.opa = opa; p.opb = opb; p.m = m; p.n = nj; p.k = k;
     p.alpha[0] = alpha[0]; p.alpha[1] = alpha[1]; p.beta[0] = beta[0]; p.beta[1] = beta[1];
     p.A = dA; p.lda = dlda;
     p.B = (opb == OP_N) ? dB + (size_t)j0 * dldb * es : dB + (size_t)j0 * es; p.ldb = dldb;
     p.C = dC + (size_t)j0 * dldc * es; p.ldc = dldc;
-    if (j == 0 && have_product) {
-      for (int cix = 0; cix < nac; ++cix) {
-        const int64_t k0 = (int64_t)cix * kch, kc = std::min<int64_t>(kch, k - k0);
-        if (kc <= 0) break;
-        { const int e = upload_a_chunk(cix); if (e) return e; }
-        B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_ac[cix], 0));
-        GemmProblem q = p;
-        q.k = kc;
-        q.A = (opa == OP_N) ? dA + (size_t)k0 * dlda * es : dA + (size_t)k0 * es;
-        q.B = (opb == OP_N) ? (const char*)p.B + (size_t)k0 * es : (const char*)p.B + (size_t)k0 * dldb * es;
-        if (cix > 0) { q.beta[0] = 1.0; q.beta[1] = 0.0; }
-        { const int e = run_device(q, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
-      }
-    } else {
-      const int e = run_device(p, st.s_comp, B200BLAS_AUTO);
-      if (e) { cudaDeviceSynchronize(); return e; }
-    }
+    return p;
+  };
+  // slab j is complete on s_comp: send its m x nj window back (rows m..ldc-1 of the caller's C stay untouched)
+  auto return_slab = [&](int j) -> int {
+    const int64_t j0 = (int64_t)j * slab, nj = std::min<int64_t>(slab, n - j0);
     B200_CUDA_TRY(cudaEventRecord(st.ev_comp[j], st.s_comp));
-    // only the m x nj window travels back: rows m..ldc-1 of the caller's C stay untouched
     if (page_c) {
       // a downloader thread drains finished slabs through the pinned ring while this thread keeps uploading
       if (!dl_started) {
@@ -295,6 +286,35 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
                                       (size_t)dldc * es, (size_t)m * es, (size_t)nj, cudaMemcpyDeviceToHost, st.s_out));
     }
     t_d2h += (uint64_t)m * nj * es;
+    return 0;
+  };
+  // Head of the pipeline: all of A has to cross the bus before ANY slab can finish (2 GiB = ~40 ms of PCIe at 16384^3, against
+  // 16 ms of arithmetic per slab), so the first `head` slabs accumulate chunk by chunk (beta = 1 after the first chunk)
+  // while the later chunks of A are still in flight: enough arithmetic to cover the whole upload of A instead of one slab's
+  // worth.  Uploads are issued in order of first use: B0 C0 A0 | B1 C1 | B2 C2 | B3 C3 | A1 | A2 ...  Later slabs see A resident
+  // and run at full k.
+  const int head = !have_product ? 0 : (nac > 1 ? std::min(nslabs, 4) : std::min(nslabs, 1));
+  for (int cix = 0; cix < nac && head > 0; ++cix) {
+    const int64_t k0 = (int64_t)cix * kch, kc = std::min<int64_t>(kch, k - k0);
+    if (kc <= 0) break;
+    for (int h = 0; h < head; ++h) {
+      if (cix == 0) { const int e = upload_slab_inputs(h); if (e) return e; }
+      if (h == 0) { const int e = upload_a_chunk(cix); if (e) return e; }
+      B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_ac[cix], 0));
+      GemmProblem q = slab_problem(h);
+      q.k = kc;
+      q.A = (opa == OP_N) ? dA + (size_t)k0 * dlda * es : dA + (size_t)k0 * es;
+      q.B = (opb == OP_N) ? (const char*)q.B + (size_t)k0 * es : (const char*)q.B + (size_t)k0 * dldb * es;
+      if (cix > 0) { q.beta[0] = 1.0; q.beta[1] = 0.0; }
+      { const int e = run_device(q, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
+      if (k0 + kc >= k) { const int e = return_slab(h); if (e) return e; }
+    }
+  }
+  for (int j = head; j < nslabs; ++j) {
+    { const int e = upload_slab_inputs(j); if (e) return e; }
+    const GemmProblem p = slab_problem(j);
+    { const int e = run_device(p, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
+    { const int e = return_slab(j); if (e) return e; }
   }
   if (dl_started) {
     downloader.join();

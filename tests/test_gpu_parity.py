@@ -310,8 +310,10 @@ def test_dmma_loader_modes_on_odd_device_pointers(L, t):
     import torch
     rng = np.random.default_rng(2468)
     cplx = t == "z"
-    m, n, k = (1500, 1100, 301) if not cplx else (801, 600, 203)
-    want_variant = "dmma_z_64x32x16_w16x16_2cta_mbar" if cplx else "dmma_d_128x64x16_w32x32_2cta_mbar"
+    # real: 17 x 21 = 357 big tiles = one full wave of 296 on the 128x64 tile + 61 tiles on the 64x32 tail launch (both
+    # configurations see the odd pointers); complex: 13 x 19 = 247 big tiles, one partial wave of the big tile only
+    m, n, k = (2100, 1300, 301) if not cplx else (801, 600, 203)
+    want_variant = "dmma_z_64x32x16_w16x16_2cta_mbar" if cplx else "dmma_d_128x64x16_w32x32_2cta_mbar+tail"
     es = 16 if cplx else 8
     rows = _sample_rows(m, 12)
     # (row offset, column offset, ld parity): odd offsets + odd ld -> 8-byte aligned only; (0, 0, even) -> 16-byte aligned
@@ -354,3 +356,44 @@ def test_dmma_loader_modes_on_odd_device_pointers(L, t):
                 _, ratio = _check(t, ta, tb, m, n, k, al, be, Asub, Bsub, Csub, gsub, Csub.shape[0], rows=rows, port_too=False)
                 worst = max(worst, ratio)
     print("dmma loader modes, worst gauge ratio", t, worst)
+
+
+@pytest.mark.parametrize("t", list("sc"))
+def test_tf32x3_huge_and_infinite_inputs(L, t):
+    """a finite value that rounds up to Inf under cvt.rna.tf32 must not overflow in the hi/lo split -- the
+    tensor variant returns the same finite numbers as the SIMT variant (= the reference's fp32 FMA path).  A true +-Inf
+    input cannot be carried through a split product (Inf * lo(b) is Inf * 0 = NaN whenever b is exactly representable);
+    the documented behaviour (include/b200blas.h) is: the affected rows come back non-finite (Inf or NaN),
+    every other row is unaffected."""
+    rng = np.random.default_rng(77)
+    m, n, k = 300, 280, 160
+    fmax = float(np.finfo(np.float32).max)
+    for case in ("huge", "inf"):
+        A = oa.rand_matrix(rng, t, m, k)
+        B = oa.rand_matrix(rng, t, k, n)
+        if case == "huge":
+            A[5, 7] = fmax * (1 - 2.0 ** -20)      # rounds UP to Inf under cvt.rna.tf32
+            A[9, 3] = -fmax
+            B[7, :] = 2.0 ** -40
+            B[3, :] = 2.0 ** -40
+        else:
+            A[5, 7] = np.inf
+            A[9, 3] = -np.inf
+        C0 = np.zeros((m, n), dtype=oa.NP_DTYPE[t], order="F")
+        outs = {}
+        for variant in ("simt", "tf32x3"):
+            L.b200blas_set_variant(eigen_b200.VARIANT[variant])
+            c = C0.copy(order="F")
+            assert oa.call_gemm(getattr(L, t + "gemm_"), t, "N", "N", m, n, k, 1.0, A, m, B, k, 0.0, c, m) == 0, eigen_b200.last_error()
+            outs[variant] = c
+        L.b200blas_set_variant(0)
+        s, x = outs["simt"], outs["tf32x3"]
+        if case == "huge":
+            assert np.isfinite(s).all() and np.isfinite(x).all(), "a finite product overflowed in the split"
+            assert np.abs(x - s).max() <= 64 * oa.EPS[t] * np.abs(s).max()
+        else:
+            bad = np.zeros(m, dtype=bool)
+            bad[[5, 9]] = True
+            assert not np.isfinite(x[bad]).any() and not np.isfinite(s[bad]).any()
+            assert np.isfinite(x[~bad]).all()
+            assert np.abs(x[~bad] - s[~bad]).max() <= 64 * oa.EPS[t] * np.abs(s[~bad]).max()
