@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
   constexpr int LDS = NBL + 1;
   extern __shared__ __align__(16) unsigned char blk_smem[];
   T* S = reinterpret_cast<T*>(blk_smem);   // S[i * LDS + j], i >= j
-  __shared__ T colbuf[2][32];
+  __shared__ T colbuf[2][64];
   const int tid = threadIdx.x;
   for (int idx = tid; idx < NBL * NBL; idx += 256) {
     int i, j;
@@ -192,44 +192,48 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
   }
   __syncthreads();
   bool ok = true;   // uniform over the CTA
+  // colbuf[p][j]: raw (unscaled) column entries of the diagonal rows; [32, 64) stays zero so that the rotated update below
+  // may read L(c0 + k + j, .) for every j without a bounds test
+  for (int idx = tid; idx < 2 * 64; idx += 256) colbuf[idx / 64][idx % 64] = Sc<T>::zero();
+  __syncthreads();
   for (int c0 = 0; c0 < NBL && c0 < d && ok; c0 += 32) {
     const int t = tid;
     const bool rowact = t < NBL - c0;
+    // the thread's row of the panel, ROTATED: a[j] = element (c0 + t, c0 + k + j) at column step k.  The column loop is a
+    // runtime loop over a compact body (the unrolled version was 120 KB of straight-line code and instruction-fetch bound)
     T a[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) a[j] = rowact ? S[(c0 + t) * LDS + c0 + j] : Sc<T>::zero();
     if (t < 32) colbuf[0][t] = a[0];
     __syncthreads();
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 32; ++k) {
-      if (ok) {
-        const R x = sc_real<T>(colbuf[k & 1][k]);
-        if (x <= (R)0) {   // a NaN pivot continues, as in the reference (LLT.h:316-317)
-          if (tid == 0) atomicMin(info, (int)(d0 + c0 + k + 1));
-          ok = false;
-        } else {
-          R l, rl;
-          pivot_roots(x, l, rl);
-          if (t == k) a[k] = sc_from_real<T>(l);
-          else if (t > k) {
-            a[k] = sc_scale<T>(a[k], rl);
-#pragma unroll
-            for (int j = k + 1; j < 32; ++j) {
-              const T ljk = sc_scale<T>(colbuf[k & 1][j], rl);   // L(c0 + j, c0 + k)
-              sc_fnma<T>(a[j], a[k], Sc<T>::conj(ljk));
-            }
-          }
-          if (k + 1 < 32) {
-            if (t < 32 && t > k) colbuf[(k + 1) & 1][t] = a[k + 1];
-            __syncthreads();
-          }
-        }
+      const T* col = colbuf[k & 1];
+      const R x = sc_real<T>(col[k]);
+      if (x <= (R)0) {   // a NaN pivot continues, as in the reference (LLT.h:316-317)
+        if (tid == 0) atomicMin(info, (int)(d0 + c0 + k + 1));
+        ok = false;
+        break;
       }
-    }
-    if (rowact) {
+      R l, rl;
+      pivot_roots(x, l, rl);
+      const bool below = rowact && t > k;
+      T lik = Sc<T>::zero();   // L(c0 + t, c0 + k)
+      if (rowact && t >= k) {
+        lik = (t == k) ? sc_from_real<T>(l) : sc_scale<T>(a[0], rl);
+        S[(c0 + t) * LDS + c0 + k] = lik;
+      }
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (t >= 32 || j <= t) S[(c0 + t) * LDS + c0 + j] = a[j];
+      for (int j = 1; j < 32; ++j) {
+        T v = a[j];
+        if (below) sc_fnma<T>(v, lik, Sc<T>::conj(sc_scale<T>(col[k + j], rl)));   // L(c0 + k + j, c0 + k); zero past the panel
+        a[j - 1] = v;
+      }
+      a[31] = Sc<T>::zero();
+      if (k + 1 < 32) {
+        if (t < 32 && t > k) colbuf[(k + 1) & 1][t] = a[0];
+        __syncthreads();
+      }
     }
     __syncthreads();
     const int c1 = c0 + 32;
@@ -731,6 +735,13 @@ struct RegPanelTables {
   T rowk[2][NBP];
 };
 
+// The column loop is a RUNTIME loop over a compact body: the rows are kept "rotated" -- the active column is always
+// element 0 of a thread's row array, and the rank-1 update writes a[j-1] = a[j] - l * u[j], shifting the row left by one --
+// so no register index depends on k.  (A fully unrolled version of this kernel is 320 KB of straight-line code; ncu showed 44 %
+// of its stall samples as "no instruction": profiles/ncu_r02_lapack_leaves.md.)  What falls off the left end is final and goes
+// to global memory at once: the multipliers l of column k (coalesced), and row k of U (known to every thread: it is the
+// pivot row everybody just received).  The interchange of the already-final L part of rows k and pivot (columns < k) is done in
+// global memory by one warp; the cluster barrier of the next column orders it against every later access.
 template <typename T, int NBP, int RPT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __restrict__ ipiv, int64_t row_base,
@@ -744,7 +755,7 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
   const int CL = (int)cluster.num_blocks(), cta = (int)cluster.block_rank(), tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   int rq[RPT];
-  T a[RPT][NBP];
+  T a[RPT][NBP];   // a[q][j] = current value of element (row rq[q], column k + j)
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
     rq[q] = (cta * RPT + q) * THREADS + tid;
@@ -753,118 +764,110 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
   }
   cluster.sync();   // every CTA's shared memory is live before anybody writes into it remotely
   const int steps = (int)min((int64_t)nb, mrows);
-  static_for<0, NBP>([&](auto kc) {
-    constexpr int k = decltype(kc)::value;
-    if (k < steps) {
-      constexpr int par = k & 1;
-      // 1. candidate of this thread / warp: largest |a(r,k)| among rows >= k, smallest row on ties (maxCoeff keeps the first)
-      double best = -1.0;
-      int brow = INT_MAX;
+#pragma unroll 1
+  for (int k = 0; k < steps; ++k) {
+    const int par = k & 1;
+    // 1. candidate of this thread / warp: largest |a(r,k)| among rows >= k, smallest row on ties (maxCoeff keeps the first)
+    double best = -1.0;
+    int brow = INT_MAX;
 #pragma unroll
-      for (int q = 0; q < RPT; ++q) {
-        if (rq[q] >= k && rq[q] < mrows) {
-          const double sc = sc_score<T>(a[q][k]);
-          if (sc > best || (sc == best && rq[q] < brow)) { best = sc; brow = rq[q]; }
-        }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-        const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
-        if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
-      }
-      if (lane == 0) { wbest[warp] = best; wrow[warp] = brow; }
-      __syncthreads();
-      // 2. the CTA's candidate (every thread reduces the warp results itself); its owner and the owner of row k publish their rows
-      double cb = -1.0;
-      int crow = INT_MAX;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        const double ob = wbest[w];
-        const int orow = wrow[w];
-        if (ob > cb || (ob == cb && orow < crow)) { cb = ob; crow = orow; }
-      }
-      const int krow_cta = k / (RPT * THREADS);   // the CTA that owns row k
-#pragma unroll
-      for (int q = 0; q < RPT; ++q) {
-        if (cb >= 0.0 && rq[q] == crow) {
-#pragma unroll
-          for (int c = 0; c < NBP; ++c) myrow[c] = a[q][c];
-        }
-        if (rq[q] == k) {
-#pragma unroll
-          for (int c = 0; c < NBP; ++c) mykrow[c] = a[q][c];
-        }
-      }
-      __syncthreads();
-      for (int idx = tid; idx < CL * NBP; idx += THREADS) {
-        const int peer = idx / NBP, c = idx % NBP;
-        RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, peer);
-        if (cb >= 0.0) rt->vals[par][cta][c] = myrow[c];
-        if (cta == krow_cta) rt->rowk[par][c] = mykrow[c];
-      }
-      if (tid < CL) {
-        RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, tid);
-        rt->score[par][cta] = cb;
-        rt->row[par][cta] = crow;
-      }
-      cluster.sync();   // release / acquire at cluster scope: the remote stores are visible
-      // 3. identical reduction of the CL candidates in every thread
-      double gb = -1.0;
-      int grow = INT_MAX, gw = -1;
-      for (int w = 0; w < CL; ++w) {
-        const double s2 = tab.score[par][w];
-        const int r2 = tab.row[par][w];
-        if (s2 >= 0.0 && (s2 > gb || (s2 == gb && r2 < grow))) { gb = s2; grow = r2; gw = w; }
-      }
-      if (gw < 0) { gb = 0.0; grow = k; }   // a column of NaNs: no candidate compares greater; treated as a zero pivot
-      const int piv = grow;
-      if (cta == 0 && tid == 0) {
-        ipiv[k] = (int)(row_base + piv + 1);
-        if (gb == 0.0) atomicMin(info, (int)(col_base + k + 1));
-      }
-      if (gb != 0.0) {
-        const T* prow = tab.vals[par][gw];
-        // 4. interchange rows k and piv (PartialPivLU.h:384-388): the two owners take over each other's contents
-        if (piv != k) {
-#pragma unroll
-          for (int q = 0; q < RPT; ++q) {
-            if (rq[q] == k) {
-#pragma unroll
-              for (int c = 0; c < NBP; ++c) a[q][c] = prow[c];
-            } else if (rq[q] == piv) {
-#pragma unroll
-              for (int c = 0; c < NBP; ++c) a[q][c] = tab.rowk[par][c];
-            }
-          }
-        }
-        // 5. scale the column below the pivot and update the rest of the panel (PartialPivLU.h:392, :404-405)
-        const T pv = prow[k];
-        T l[RPT];
-        bool act[RPT];
-#pragma unroll
-        for (int q = 0; q < RPT; ++q) {
-          l[q] = Sc<T>::zero();
-          act[q] = rq[q] > k && rq[q] < mrows;
-          if (act[q]) { l[q] = sc_div<T>(a[q][k], pv); a[q][k] = l[q]; }
-        }
-#pragma unroll
-        for (int j = k + 1; j < NBP; ++j) {
-          const T u = prow[j];
-#pragma unroll
-          for (int q = 0; q < RPT; ++q)
-            if (act[q]) sc_fnma<T>(a[q][j], l[q], u);
-        }
+    for (int q = 0; q < RPT; ++q) {
+      if (rq[q] >= k && rq[q] < mrows) {
+        const double sc = sc_score<T>(a[q][0]);
+        if (sc > best || (sc == best && rq[q] < brow)) { best = sc; brow = rq[q]; }
       }
     }
-  });
 #pragma unroll
-  for (int q = 0; q < RPT; ++q) {
-    if (rq[q] < mrows) {
-#pragma unroll
-      for (int c = 0; c < NBP; ++c)
-        if (c < nb) A[rq[q] + (int64_t)c * lda] = a[q][c];
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
+      if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
     }
+    if (lane == 0) { wbest[warp] = best; wrow[warp] = brow; }
+    __syncthreads();
+    // 2. the CTA's candidate (every thread reduces the warp results itself); its owner and the owner of row k publish their rows
+    double cb = -1.0;
+    int crow = INT_MAX;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const double ob = wbest[w];
+      const int orow = wrow[w];
+      if (ob > cb || (ob == cb && orow < crow)) { cb = ob; crow = orow; }
+    }
+    const int krow_cta = k / (RPT * THREADS);   // the CTA that owns row k
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      if (cb >= 0.0 && rq[q] == crow) {
+#pragma unroll
+        for (int c = 0; c < NBP; ++c) myrow[c] = a[q][c];
+      }
+      if (rq[q] == k) {
+#pragma unroll
+        for (int c = 0; c < NBP; ++c) mykrow[c] = a[q][c];
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < CL * NBP; idx += THREADS) {
+      const int peer = idx / NBP, c = idx % NBP;
+      RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, peer);
+      if (cb >= 0.0) rt->vals[par][cta][c] = myrow[c];
+      if (cta == krow_cta) rt->rowk[par][c] = mykrow[c];
+    }
+    if (tid < CL) {
+      RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, tid);
+      rt->score[par][cta] = cb;
+      rt->row[par][cta] = crow;
+    }
+    cluster.sync();   // release / acquire at cluster scope: the remote stores (and the global stores of the previous column) are visible
+    // 3. identical reduction of the CL candidates in every thread
+    double gb = -1.0;
+    int grow = INT_MAX, gw = -1;
+    for (int w = 0; w < CL; ++w) {
+      const double s2 = tab.score[par][w];
+      const int r2 = tab.row[par][w];
+      if (s2 >= 0.0 && (s2 > gb || (s2 == gb && r2 < grow))) { gb = s2; grow = r2; gw = w; }
+    }
+    if (gw < 0) { gb = 0.0; grow = k; }   // a column of NaNs: no candidate compares greater; treated as a zero pivot
+    const bool nonzero = gb != 0.0;       // zero pivot column: recorded and skipped (PartialPivLU.h:396-401)
+    const int piv = nonzero ? grow : k;
+    const T* urow = nonzero ? tab.vals[par][gw] : tab.rowk[par];   // row k of U, in rotated coordinates (urow[j] = U(k, k + j))
+    if (cta == 0 && tid == 0) {
+      ipiv[k] = (int)(row_base + piv + 1);
+      if (!nonzero) atomicMin(info, (int)(col_base + k + 1));
+    }
+    // row k is final: U(k, k..nb) goes to global memory, and the finished L part (columns < k <= 32) of rows k and piv is
+    // interchanged there -- by one warp, lane c = column c; its two loads are issued here and consumed after the update below
+    static_assert(NBP <= 32, "one lane per panel column");
+    const bool helper = cta == 0 && warp == 1;
+    const bool swap_l = helper && piv != k && lane < k;
+    T t1 = Sc<T>::zero(), t2 = Sc<T>::zero();
+    if (helper && k + lane < nb) A[k + (int64_t)(k + lane) * lda] = urow[lane];
+    if (swap_l) { t1 = __ldcg(&A[k + (int64_t)lane * lda]); t2 = __ldcg(&A[piv + (int64_t)lane * lda]); }
+    const T pv = urow[0];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+      // 4. interchange rows k and piv (PartialPivLU.h:384-388): the owner of position piv takes over the old row k
+      if (piv != k && rq[q] == piv) {
+#pragma unroll
+        for (int c = 0; c < NBP; ++c) a[q][c] = tab.rowk[par][c];
+      }
+      // 5. scale the column below the pivot, store it, update the rest of the row and rotate it (PartialPivLU.h:392, :404-405)
+      const bool act = rq[q] > k && rq[q] < mrows;
+      T l = Sc<T>::zero();
+      if (act) {
+        l = nonzero ? sc_div<T>(a[q][0], pv) : a[q][0];
+        A[rq[q] + (int64_t)k * lda] = l;
+        if (!nonzero) l = Sc<T>::zero();
+      }
+#pragma unroll
+      for (int j = 1; j < NBP; ++j) {
+        T v = a[q][j];
+        if (act) sc_fnma<T>(v, l, urow[j]);
+        a[q][j - 1] = v;
+      }
+      a[q][NBP - 1] = Sc<T>::zero();
+    }
+    if (swap_l) { A[k + (int64_t)lane * lda] = t2; A[piv + (int64_t)lane * lda] = t1; }
   }
   cluster.sync();   // nobody exits while a peer may still write into its tables
 }

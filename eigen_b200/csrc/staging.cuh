@@ -99,7 +99,10 @@ inline CopyPool& copy_pool() {
     int n = e ? atoi(e) : 0;
     if (n <= 0) {
       const unsigned hc = std::thread::hardware_concurrency();
-      n = hc >= 32 ? 12 : hc >= 16 ? 7 : hc >= 8 ? 5 : hc >= 4 ? 3 : 1;
+      // the caller is blocked inside a BLAS call, so its cores are free to copy: measured on a 16-core B200 host
+      // (profiles/bench_r02/e2e_copy_threads_pass5.jsonl, dgemm 16384^3 from pageable memory): 7 threads 27.1, 12 threads 29.5,
+      // 16 threads 29.9 TFLOP/s
+      n = hc >= 16 ? 16 : hc >= 8 ? (int)hc - 2 : hc >= 4 ? 3 : 1;
     }
     return n - 1 < 0 ? 0 : n - 1;  // the calling thread is the n-th copier
   }());

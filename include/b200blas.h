@@ -115,7 +115,12 @@ int zher2k_(const char* uplo, const char* trans, const int* n, const int* k, con
  *   info -1 bad uplo | -2 n<0 | -4 lda<max(1,n) (-> xerbla_("xPOTRF", &(-info), 6)); info = k > 0: the leading minor of
  *   order k is not positive definite.  lapack/cholesky.cpp:14-38, Eigen/src/Cholesky/LLT.h:299-360.
  * ?getrf_: P A = L U with partial pivoting, ipiv 1-based; info -1 m<0 | -2 n<0 | -4 lda<max(1,m); info = k > 0: U(k,k) is
- *   exactly zero (the factorization is completed).  lapack/lu.cpp:14-42, Eigen/src/LU/PartialPivLU.h:361-496. */
+ *   exactly zero (the factorization is completed).  lapack/lu.cpp:14-42, Eigen/src/LU/PartialPivLU.h:361-496.
+ *   No row limit: panels of up to 16384 rows run on the register-resident cluster kernel, taller ones on the cooperative
+ *   slab kernel (shared memory, or a global-memory slab above ~120k rows of doubles); tests/test_gpu_lapack.py covers each.
+ * Both run a right-looking blocked loop with one step of look-ahead on an internal high-priority stream; the call is still
+ * ordered on the caller's stream (device pointers) / synchronous (host pointers).  Environment (forced variants for A/B
+ * runs): B200BLAS_LOOKAHEAD=0, B200BLAS_POTRF=rec, B200BLAS_GETRF=rec, B200BLAS_GETF2=reg|slab|cluster, B200BLAS_TRSM=inv|subst. */
 int spotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info);
 int dpotrf_(const char* uplo, const int* n, double* a, const int* lda, int* info);
 int cpotrf_(const char* uplo, const int* n, float* a, const int* lda, int* info);
@@ -138,6 +143,10 @@ enum { B200BLAS_S = 0, B200BLAS_D = 1, B200BLAS_C = 2, B200BLAS_Z = 3 };
 /* kernel variants (b200blas_gemm_dev's variant argument, env B200BLAS_VARIANT=auto|simt|dmma|tf32x3) */
 enum { B200BLAS_AUTO = 0, B200BLAS_SIMT = 1, B200BLAS_DMMA = 2, B200BLAS_TF32X3 = 3 };
 
+/* Non-finite inputs on the float tensor path (type S / C, variant tf32x3): every operand is split as x = hi + lo (3xTF32).  A
+ * finite x always stays finite (values that would round up to Inf are truncated instead), NaN propagates, but a +-Inf input
+ * makes the affected rows / columns of the result non-finite (Inf or NaN: Inf * lo(b) is Inf * 0 whenever b is exactly
+ * representable in tf32) where the reference's fp32 FMA path returns +-Inf.  B200BLAS_VARIANT=simt keeps IEEE behaviour. */
 int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, const void* alpha, const void* dA,
                       int64_t lda, const void* dB, int64_t ldb, const void* beta, void* dC, int64_t ldc,
                       void* stream, int variant);
