@@ -84,6 +84,7 @@ int launch_trmm(const TriProblem& p, cudaStream_t s);
 int trsm_leaf_order(int type);                                            // order of the diagonal blocks TriProblem::Vinv holds
 int launch_trtri_diag(const TriProblem& p, void* V, cudaStream_t s);      // fills such a Vinv for p's triangle
 bool trsm_substitution_forced();                                          // B200BLAS_TRSM=subst
+bool trsm_inverse_forced();                                               // B200BLAS_TRSM=inv
 size_t symm_workspace_bytes(const SymmProblem& p);
 int launch_symm(const SymmProblem& p, cudaStream_t s, void* workspace);
 int launch_potrf(const PotrfProblem& p, cudaStream_t s);   // lapack.cu

@@ -217,6 +217,15 @@ dmma_gemm_kernel(PanelSrc a, PanelSrc b, int64_t m, int64_t n, int64_t k, double
     if constexpr (TRI) return in_triangle(ep.uplo, i, j); else return true;
   };
 
+  // short k (rank-k updates: config C5, the trailing updates of ?potrf_ / ?getrf_): the read-modify-write of the C tile in the
+  // epilogue is a full HBM round trip that nothing overlaps once the k loop is over -- request the tile's lines into L2 now
+  if (!ep.beta_zero && k <= 1024) {
+    constexpr int LINES_PER_COL = C::BM / 16, NCOLS = C::BN / SC;   // BM * 8 bytes per column = BM / 16 lines of 128 bytes
+    for (int line = tid; line < LINES_PER_COL * NCOLS; line += C::THREADS) {
+      const int64_t gi = m0 + (int64_t)(line % LINES_PER_COL) * (16 / SC), gj = n0 + line / LINES_PER_COL;
+      if (gi < m && gj < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(Cmat + SC * (gi + gj * ldc)));
+    }
+  }
   constexpr int BK = C::BK, STAGES = C::STAGES;
   using LA = Loader<C::BM, C::THREADS, CPLX, BK, AMODE, C::LDA_S>;
   using LB = Loader<C::BN, C::THREADS, CPLX, BK, BMODE, C::LDB_S>;

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
   constexpr int LDS = NBL + 1;
   extern __shared__ __align__(16) unsigned char blk_smem[];
   T* S = reinterpret_cast<T*>(blk_smem);   // S[i * LDS + j], i >= j
-  __shared__ T colbuf[2][64];
+  __shared__ T colbuf[3][64];
   const int tid = threadIdx.x;
   for (int idx = tid; idx < NBL * NBL; idx += 256) {
     int i, j;
@@ -192,9 +192,9 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
   }
   __syncthreads();
   bool ok = true;   // uniform over the CTA
-  // colbuf[p][j]: raw (unscaled) column entries of the diagonal rows; [32, 64) stays zero so that the rotated update below
-  // may read L(c0 + k + j, .) for every j without a bounds test
-  for (int idx = tid; idx < 2 * 64; idx += 256) colbuf[idx / 64][idx % 64] = Sc<T>::zero();
+  // colbuf[p][j]: raw (unscaled) entries of the current column in the diagonal rows, three buffers in rotation; [32, 64) stays
+  // zero so that the rotated update below may read L(c0 + k + j, .) for every j without a bounds test
+  for (int idx = tid; idx < 3 * 64; idx += 256) colbuf[idx / 64][idx % 64] = Sc<T>::zero();
   __syncthreads();
   for (int c0 = 0; c0 < NBL && c0 < d && ok; c0 += 32) {
     const int t = tid;
@@ -206,34 +206,44 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
     for (int j = 0; j < 32; ++j) a[j] = rowact ? S[(c0 + t) * LDS + c0 + j] : Sc<T>::zero();
     if (t < 32) colbuf[0][t] = a[0];
     __syncthreads();
+    // Critical path of a column = barrier -> pivot x -> 1/x -> update of the NEXT column's entry -> publish -> barrier:
+    // the update uses w = a(i,k) / x against the RAW column (a(i,j) -= w * conj(a(j,k)), the same product as
+    // L(i,k) conj(L(j,k))), so neither the square root nor the scaled column is on that path; the roots, the stored L entries
+    // and the other 30 updates of the row are issued after the barrier, under the next column's latency.
+    R x = sc_real<T>(colbuf[0][0]);
+    R inv_x = (R)1 / x;
 #pragma unroll 1
     for (int k = 0; k < 32; ++k) {
-      const T* col = colbuf[k & 1];
-      const R x = sc_real<T>(col[k]);
       if (x <= (R)0) {   // a NaN pivot continues, as in the reference (LLT.h:316-317)
         if (tid == 0) atomicMin(info, (int)(d0 + c0 + k + 1));
         ok = false;
         break;
       }
+      const T* col = colbuf[k % 3];
+      const bool below = rowact && t > k;
+      const T a0 = a[0];
+      const T w = below ? sc_scale<T>(a0, inv_x) : Sc<T>::zero();
+      T v1 = a[1];
+      sc_fnma<T>(v1, w, Sc<T>::conj(col[k + 1]));
+      R xn = (R)1, inv_xn = (R)1;
+      if (k + 1 < 32) {
+        if (t < 32 && t > k) colbuf[(k + 1) % 3][t] = v1;
+        __syncthreads();
+        xn = sc_real<T>(colbuf[(k + 1) % 3][k + 1]);
+        inv_xn = (R)1 / xn;
+      }
       R l, rl;
       pivot_roots(x, l, rl);
-      const bool below = rowact && t > k;
-      T lik = Sc<T>::zero();   // L(c0 + t, c0 + k)
-      if (rowact && t >= k) {
-        lik = (t == k) ? sc_from_real<T>(l) : sc_scale<T>(a[0], rl);
-        S[(c0 + t) * LDS + c0 + k] = lik;
-      }
+      if (rowact && t >= k) S[(c0 + t) * LDS + c0 + k] = (t == k) ? sc_from_real<T>(l) : sc_scale<T>(a0, rl);   // L(c0 + t, c0 + k)
+      a[0] = v1;
 #pragma unroll
-      for (int j = 1; j < 32; ++j) {
+      for (int j = 2; j < 32; ++j) {
         T v = a[j];
-        if (below) sc_fnma<T>(v, lik, Sc<T>::conj(sc_scale<T>(col[k + j], rl)));   // L(c0 + k + j, c0 + k); zero past the panel
+        sc_fnma<T>(v, w, Sc<T>::conj(col[k + j]));   // raw a(c0 + k + j, c0 + k); zero past the panel
         a[j - 1] = v;
       }
       a[31] = Sc<T>::zero();
-      if (k + 1 < 32) {
-        if (t < 32 && t > k) colbuf[(k + 1) & 1][t] = a[0];
-        __syncthreads();
-      }
+      x = xn; inv_x = inv_xn;
     }
     __syncthreads();
     const int c1 = c0 + 32;
@@ -738,16 +748,35 @@ struct RegPanelTables {
 // The column loop is a RUNTIME loop over a compact body: the rows are kept "rotated" -- the active column is always
 // element 0 of a thread's row array, and the rank-1 update writes a[j-1] = a[j] - l * u[j], shifting the row left by one --
 // so no register index depends on k.  (A fully unrolled version of this kernel is 320 KB of straight-line code; ncu showed 44 %
-// of its stall samples as "no instruction": profiles/ncu_r02_lapack_leaves.md.)  What falls off the left end is final and goes
-// to global memory at once: the multipliers l of column k (coalesced), and row k of U (known to every thread: it is the
-// pivot row everybody just received).  The interchange of the already-final L part of rows k and pivot (columns < k) is done in
-// global memory by one warp; the cluster barrier of the next column orders it against every later access.
+// of its stall samples as "no instruction": profiles/ncu_r02_lapack_leaves.md.)  What falls off the left end is final: the
+// multipliers l of column k go to a shared-memory column buffer (Lbuf), row k of U -- known to every thread: it is the pivot
+// row everybody just received -- to a buffer in CTA 0; both are flushed to global memory once, after the last column, so
+// that the per-column cluster barrier never has to wait for global stores (the version that stored them at once spent 15 %
+// of its stall samples in the barrier's fence).  The interchange of the already-final L part of rows k and pivot (columns
+// < k) is done on the Lbuf columns, through distributed shared memory, by one warp.  All reductions are shuffle trees
+// (max of the scores, then the smallest row among the lanes that hold the maximum = maxCoeff's "first").
+__device__ __forceinline__ void argmax_tree(double& best, int& brow) {   // warp-wide: largest score, smallest row on ties
+  double m = best;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double o = __shfl_xor_sync(0xffffffffu, m, off);
+    m = o > m ? o : m;
+  }
+  brow = (int)__reduce_min_sync(0xffffffffu, (unsigned)((best == m) ? brow : INT_MAX));
+  best = m;
+}
+
 template <typename T, int NBP, int RPT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __restrict__ ipiv, int64_t row_base,
                  int* __restrict__ info, int64_t col_base) {
-  constexpr int NW = THREADS / 32;
+  constexpr int NW = THREADS / 32, RT = RPT * THREADS;
+  static_assert(NW <= 32 && NBP <= 32, "one lane per warp result / per panel column");
+  extern __shared__ __align__(16) unsigned char reg_smem[];
+  T* Lbuf = reinterpret_cast<T*>(reg_smem);   // Lbuf[c * RT + local row]: multipliers of column c, this CTA's rows
   __shared__ RegPanelTables<T, NBP> tab;
+  __shared__ T Ubuf[NBP][NBP];                // CTA 0: Ubuf[k][j] = U(k, k + j)
+  __shared__ int ipiv_s[NBP];                 // CTA 0
   __shared__ double wbest[NW];
   __shared__ int wrow[NW];
   __shared__ T myrow[NBP], mykrow[NBP];
@@ -758,7 +787,7 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
   T a[RPT][NBP];   // a[q][j] = current value of element (row rq[q], column k + j)
 #pragma unroll
   for (int q = 0; q < RPT; ++q) {
-    rq[q] = (cta * RPT + q) * THREADS + tid;
+    rq[q] = cta * RT + q * THREADS + tid;
 #pragma unroll
     for (int c = 0; c < NBP; ++c) a[q][c] = (rq[q] < mrows && c < nb) ? A[rq[q] + (int64_t)c * lda] : Sc<T>::zero();
   }
@@ -767,34 +796,24 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
 #pragma unroll 1
   for (int k = 0; k < steps; ++k) {
     const int par = k & 1;
-    // 1. candidate of this thread / warp: largest |a(r,k)| among rows >= k, smallest row on ties (maxCoeff keeps the first)
+    // 1. candidate of this thread -> warp: largest |a(r,k)| among rows >= k, smallest row on ties (maxCoeff keeps the first)
     double best = -1.0;
     int brow = INT_MAX;
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       if (rq[q] >= k && rq[q] < mrows) {
         const double sc = sc_score<T>(a[q][0]);
-        if (sc > best || (sc == best && rq[q] < brow)) { best = sc; brow = rq[q]; }
+        if (sc > best) { best = sc; brow = rq[q]; }   // rq[0] < rq[1]: the first row wins a tie
       }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-      const int orow = __shfl_xor_sync(0xffffffffu, brow, off);
-      if (ob > best || (ob == best && orow < brow)) { best = ob; brow = orow; }
-    }
+    argmax_tree(best, brow);
     if (lane == 0) { wbest[warp] = best; wrow[warp] = brow; }
     __syncthreads();
-    // 2. the CTA's candidate (every thread reduces the warp results itself); its owner and the owner of row k publish their rows
-    double cb = -1.0;
-    int crow = INT_MAX;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const double ob = wbest[w];
-      const int orow = wrow[w];
-      if (ob > cb || (ob == cb && orow < crow)) { cb = ob; crow = orow; }
-    }
-    const int krow_cta = k / (RPT * THREADS);   // the CTA that owns row k
+    // 2. warp results -> the CTA's candidate (every warp runs the same tree); its owner and the owner of row k publish their rows
+    double cb = lane < NW ? wbest[lane] : -1.0;
+    int crow = lane < NW ? wrow[lane] : INT_MAX;
+    argmax_tree(cb, crow);
+    const int krow_cta = k / RT;   // the CTA that owns row k
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       if (cb >= 0.0 && rq[q] == crow) {
@@ -818,32 +837,39 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
       rt->score[par][cta] = cb;
       rt->row[par][cta] = crow;
     }
-    cluster.sync();   // release / acquire at cluster scope: the remote stores (and the global stores of the previous column) are visible
-    // 3. identical reduction of the CL candidates in every thread
+    cluster.sync();   // release / acquire at cluster scope: the remote stores of this column are visible
+    // 3. identical reduction of the CL candidates in every warp
     double gb = -1.0;
-    int grow = INT_MAX, gw = -1;
-    for (int w = 0; w < CL; ++w) {
-      const double s2 = tab.score[par][w];
-      const int r2 = tab.row[par][w];
-      if (s2 >= 0.0 && (s2 > gb || (s2 == gb && r2 < grow))) { gb = s2; grow = r2; gw = w; }
+    int grow = INT_MAX;
+    if (lane < CL) {
+      const double s2 = tab.score[par][lane];
+      if (s2 >= 0.0) { gb = s2; grow = tab.row[par][lane]; }
     }
-    if (gw < 0) { gb = 0.0; grow = k; }   // a column of NaNs: no candidate compares greater; treated as a zero pivot
-    const bool nonzero = gb != 0.0;       // zero pivot column: recorded and skipped (PartialPivLU.h:396-401)
-    const int piv = nonzero ? grow : k;
-    const T* urow = nonzero ? tab.vals[par][gw] : tab.rowk[par];   // row k of U, in rotated coordinates (urow[j] = U(k, k + j))
+    const int my_row = grow;
+    argmax_tree(gb, grow);
+    const bool nonzero = gb > 0.0;        // zero (or all-NaN) pivot column: recorded and skipped (PartialPivLU.h:396-401)
+    const int gw = __ffs(__ballot_sync(0xffffffffu, my_row == grow && grow != INT_MAX)) - 1;   // the CTA that holds the winner
+    const int piv = (nonzero && gw >= 0) ? grow : k;
+    const bool have = nonzero && gw >= 0;
+    const T* urow = have ? tab.vals[par][gw] : tab.rowk[par];   // row k of U, in rotated coordinates (urow[j] = U(k, k + j))
     if (cta == 0 && tid == 0) {
-      ipiv[k] = (int)(row_base + piv + 1);
-      if (!nonzero) atomicMin(info, (int)(col_base + k + 1));
+      ipiv_s[k] = (int)(row_base + piv + 1);
+      if (!have) atomicMin(info, (int)(col_base + k + 1));
     }
-    // row k is final: U(k, k..nb) goes to global memory, and the finished L part (columns < k <= 32) of rows k and piv is
-    // interchanged there -- by one warp, lane c = column c; its two loads are issued here and consumed after the update below
-    static_assert(NBP <= 32, "one lane per panel column");
+    // row k is final: U(k, k..) is kept in CTA 0; the finished L part (columns < k) of rows k and piv is interchanged in the
+    // Lbuf columns of their owners, by one warp (lane c = column c); its loads are issued here and consumed after the update
     const bool helper = cta == 0 && warp == 1;
     const bool swap_l = helper && piv != k && lane < k;
     T t1 = Sc<T>::zero(), t2 = Sc<T>::zero();
-    if (helper && k + lane < nb) A[k + (int64_t)(k + lane) * lda] = urow[lane];
-    if (swap_l) { t1 = __ldcg(&A[k + (int64_t)lane * lda]); t2 = __ldcg(&A[piv + (int64_t)lane * lda]); }
-    const T pv = urow[0];
+    T* lk = nullptr;
+    T* lp = nullptr;
+    if (helper && lane < NBP) Ubuf[k][lane] = urow[lane];
+    if (swap_l) {
+      lk = cluster.map_shared_rank(Lbuf, k / RT) + (size_t)lane * RT + k % RT;
+      lp = cluster.map_shared_rank(Lbuf, piv / RT) + (size_t)lane * RT + piv % RT;
+      t1 = *lk; t2 = *lp;
+    }
+    const T inv_pv = have ? sc_recip<T>(urow[0]) : Sc<T>::zero();
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       // 4. interchange rows k and piv (PartialPivLU.h:384-388): the owner of position piv takes over the old row k
@@ -851,25 +877,42 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
 #pragma unroll
         for (int c = 0; c < NBP; ++c) a[q][c] = tab.rowk[par][c];
       }
-      // 5. scale the column below the pivot, store it, update the rest of the row and rotate it (PartialPivLU.h:392, :404-405)
+      // 5. scale the column below the pivot, keep it, update the rest of the row and rotate it (PartialPivLU.h:392, :404-405).
+      //    Rows that take no part (<= k, or past the panel) get l = 0; their registers are dead from here on.
       const bool act = rq[q] > k && rq[q] < mrows;
       T l = Sc<T>::zero();
       if (act) {
-        l = nonzero ? sc_div<T>(a[q][0], pv) : a[q][0];
-        A[rq[q] + (int64_t)k * lda] = l;
-        if (!nonzero) l = Sc<T>::zero();
+        l = have ? Sc<T>::mul(a[q][0], inv_pv) : a[q][0];
+        Lbuf[(size_t)k * RT + q * THREADS + tid] = l;
+        if (!have) l = Sc<T>::zero();
       }
 #pragma unroll
       for (int j = 1; j < NBP; ++j) {
         T v = a[q][j];
-        if (act) sc_fnma<T>(v, l, urow[j]);
+        sc_fnma<T>(v, l, urow[j]);
         a[q][j - 1] = v;
       }
       a[q][NBP - 1] = Sc<T>::zero();
     }
-    if (swap_l) { A[k + (int64_t)lane * lda] = t2; A[piv + (int64_t)lane * lda] = t1; }
+    if (swap_l) { *lk = t2; *lp = t1; }
   }
-  cluster.sync();   // nobody exits while a peer may still write into its tables
+  cluster.sync();   // every multiplier and every interchange has landed in its Lbuf
+  // flush: L part of this CTA's rows (coalesced), and from CTA 0 the U rows and the pivots
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (rq[q] < mrows) {
+      const int ncol = min(rq[q], steps);   // columns c < r (and < steps) hold L(r, c)
+      for (int c = 0; c < ncol; ++c) A[rq[q] + (int64_t)c * lda] = Lbuf[(size_t)c * RT + q * THREADS + tid];
+    }
+  }
+  if (cta == 0) {
+    for (int idx = tid; idx < steps * NBP; idx += THREADS) {
+      const int k = idx / NBP, j = idx % NBP;
+      if (k + j < nb) A[k + (int64_t)(k + j) * lda] = Ubuf[k][j];
+    }
+    if (tid < steps) ipiv[tid] = ipiv_s[tid];
+  }
+  cluster.sync();   // nobody exits while a peer may still access its shared memory
 }
 
 // ---- row interchanges as a permutation -----------------------------------------------------------------------------------
@@ -1056,7 +1099,9 @@ int launch_reg_panel(int64_t mrows, int nb, T* A, int64_t lda, int* ipiv, int64_
   int cl = (int)((mrows + (int64_t)REG_THREADS * RPT - 1) / ((int64_t)REG_THREADS * RPT));
   if (cl < 1) cl = 1;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(cl); cfg.blockDim = dim3(REG_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  constexpr size_t lbuf_bytes = (size_t)NBP * RPT * REG_THREADS * sizeof(T);   // 128 KB in every configuration
+  B200_SET_MAX_DYN_SMEM_ONCE(kern, lbuf_bytes);
+  cfg.gridDim = dim3(cl); cfg.blockDim = dim3(REG_THREADS); cfg.dynamicSmemBytes = lbuf_bytes; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1155,9 +1200,9 @@ int getrf_rec(const GetrfProblem& p, const GetrfCtx& cx, int64_t j0, int64_t nc,
   return apply_pivots<T>(p, cx, j0 + n1, n2, j0, n1, s);                 // interchanges of the right half -> left half
 }
 
-// B := inv(L11) * B for the unit-lower jb x jb block at the top of panel j0, B = jb x ncols at column c0: one product on the
-// tensor-pipe kernels against the block's inverse (Vinv, from launch_trtri_diag) plus a copy back, or -- B200BLAS_TRSM=subst --
-// the substitution leaf (PartialPivLU.h:490)
+// B := inv(L11) * B for the unit-lower jb x jb block at the top of panel j0, B = jb x ncols at column c0 (PartialPivLU.h:490):
+// one launch of the shared-memory block solve (tri.cu), or -- B200BLAS_TRSM=inv -- one product on the tensor-pipe kernels
+// against the block's inverse (Vinv, from launch_trtri_diag) plus a copy back
 template <typename T>
 int panel_row_solve(const GetrfProblem& p, int64_t j0, int64_t jb, int64_t c0, int64_t ncols, const void* Vinv, void* Xtmp, cudaStream_t s) {
   if (ncols <= 0) return 0;
@@ -1166,7 +1211,7 @@ int panel_row_solve(const GetrfProblem& p, int64_t j0, int64_t jb, int64_t c0, i
   t.type = p.type; t.left = 1; t.uplo = UPLO_LOWER; t.op = OP_N; t.unit = 1; t.m = jb; t.n = ncols;
   t.alpha[0] = 1.0; t.alpha[1] = 0.0;
   t.A = A + j0 + j0 * p.lda; t.lda = p.lda; t.B = A + j0 + c0 * p.lda; t.ldb = p.lda;
-  if (!trsm_substitution_forced()) { t.Vinv = Vinv; t.Xtmp = Xtmp; }
+  if (trsm_inverse_forced()) { t.Vinv = Vinv; t.Xtmp = Xtmp; }   // default: the shared-memory block solve of tri.cu (one launch, in place)
   return launch_trsm(t, s);
 }
 // A[r0.., c0..c0+ncols) -= A[r0.., j0..j0+jb) * A[j0..j0+jb, c0..c0+ncols)   (PartialPivLU.h:492)
@@ -1218,7 +1263,7 @@ int getrf_blocked(const GetrfProblem& p, const GetrfCtx& cx, const GetrfCtx& cx2
       TriProblem t;
       t.type = p.type; t.left = 1; t.uplo = UPLO_LOWER; t.op = OP_N; t.unit = 1; t.m = jb; t.n = 1;
       t.A = (T*)p.A + j + j * p.lda; t.lda = p.lda;
-      if (!trsm_substitution_forced()) B200_CUDA_TRY(launch_trtri_diag(t, Vinv, sp));
+      if (trsm_inverse_forced()) B200_CUDA_TRY(launch_trtri_diag(t, Vinv, sp));
     }
     if (look) B200_CUDA_TRY(cudaEventRecord(la.e_panel, sp));
     if (nb2 > 0) {   // next block column on the panel stream

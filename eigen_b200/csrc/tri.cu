@@ -164,6 +164,114 @@ tri_leaf_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrhs, cons
   }
 }
 
+// ---- block solve: S x = b for a LOWER canonical S of order <= LB, right-hand sides staged in shared memory -------------------------
+// The substitution leaf above gives every thread one whole right-hand side (128 dependent steps per thread, strided global
+// accesses for side = left: 42 - 70 us per launch).  Here a CTA owns NV right-hand sides as a tile X[i][v] in shared memory and
+// walks the triangle in blocks of 32 rows: (1) the rows of the block are updated with the already solved part by ALL threads
+// (4 x 2 register tiles, S broadcast from shared memory), (2) the 32 x 32 diagonal block is solved by one thread per
+// right-hand side with the row ROTATED through registers (x[0] is always the next unknown; a compact runtime loop instead of
+// 500 unrolled FMAs).  Used for every solve whose canonical matrix is lower (left: lower/N, upper/T,C; right: upper/N,
+// lower/T,C) -- in particular the panel solves of ?potrf_ and the row solves of ?getrf_.
+template <typename T, int LB, int NV>
+__global__ void __launch_bounds__(256)
+tri_block_solve_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrhs, const T* __restrict__ A, int64_t lda,
+                       T* B, int64_t ldb) {
+  constexpr int LDSS = LB + 1, LDX = NV + 1;
+  extern __shared__ __align__(16) unsigned char bs_smem[];
+  T* S = reinterpret_cast<T*>(bs_smem);   // S[i * LDSS + j], lower canonical, reciprocal diagonal
+  T* X = S + LB * LDSS;                    // X[i * LDX + v]
+  const int tid = threadIdx.x;
+  const bool swap = left ? (op != OP_N) : (op == OP_N);
+  for (int idx = tid; idx < LB * LB; idx += 256) {
+    const int r = idx % LB, c = idx / LB;   // element of A (coalesced along r)
+    const bool referenced = r < nb && c < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
+    T v = (r == c) ? sc_one<T>() : Sc<T>::zero();
+    if (referenced) {
+      v = A[r + (int64_t)c * lda];
+      if (op == OP_C) v = Sc<T>::conj(v);
+      if (r == c) v = sc_recip<T>(v);
+    }
+    const int i = swap ? c : r, j = swap ? r : c;
+    S[i * LDSS + j] = v;
+  }
+  const int64_t v0 = (int64_t)blockIdx.x * NV;
+  const int nv = (int)min((int64_t)NV, nrhs - v0);
+  if (left) {
+    for (int idx = tid; idx < LB * NV; idx += 256) {
+      const int i = idx % LB, v = idx / LB;
+      X[i * LDX + v] = (i < nb && v < nv) ? B[i + (v0 + v) * ldb] : Sc<T>::zero();
+    }
+  } else {
+    for (int idx = tid; idx < LB * NV; idx += 256) {
+      const int v = idx % NV, i = idx / NV;
+      X[i * LDX + v] = (i < nb && v < nv) ? B[(v0 + v) + (int64_t)i * ldb] : Sc<T>::zero();
+    }
+  }
+  __syncthreads();
+  const int nblk = (nb + 31) / 32;
+  for (int b = 0; b < nblk; ++b) {
+    const int r0 = 32 * b;
+    if (b > 0) {
+      // (1) X[r0 + ii][v] -= sum_{q < r0} S[r0 + ii][q] X[q][v]: 32 x NV outputs, 4 rows x (NV / 32) vectors per thread
+      constexpr int VT = NV / 32;
+      const int tr = (tid / 32) * 4, tv = tid % 32;   // rows r0 + tr .. + 3, vectors tv + 32 * e
+      T acc[4][VT];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < VT; ++e) acc[r][e] = X[(r0 + tr + r) * LDX + tv + 32 * e];
+      const T* srow = S + (r0 + tr) * LDSS;
+#pragma unroll 4
+      for (int q = 0; q < r0; ++q) {
+        T sv[4], xv[VT];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) sv[r] = srow[r * LDSS + q];          // warp-wide broadcasts
+#pragma unroll
+        for (int e = 0; e < VT; ++e) xv[e] = X[q * LDX + tv + 32 * e];  // consecutive lanes, consecutive words
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int e = 0; e < VT; ++e) sc_fnma<T>(acc[r][e], sv[r], xv[e]);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < VT; ++e) X[(r0 + tr + r) * LDX + tv + 32 * e] = acc[r][e];
+      __syncthreads();
+    }
+    // (2) diagonal block: one thread per right-hand side, rotated row
+    if (tid < NV) {
+      T x[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = X[(r0 + i) * LDX + tid];
+#pragma unroll 1
+      for (int q = 0; q < 32; ++q) {
+        const T* scol = S + (r0 + q) * LDSS + r0 + q;   // S[r0 + q + i][r0 + q] = scol[i * LDSS]
+        const T xq = Sc<T>::mul(x[0], scol[0]);        // reciprocal diagonal (1 for unit / identity rows)
+        X[(r0 + q) * LDX + tid] = xq;
+#pragma unroll
+        for (int i = 1; i < 32; ++i) {
+          T v = x[i];
+          if (q + i < 32) sc_fnma<T>(v, scol[i * LDSS], xq);
+          x[i - 1] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (left) {
+    for (int idx = tid; idx < LB * NV; idx += 256) {
+      const int i = idx % LB, v = idx / LB;
+      if (i < nb && v < nv) B[i + (v0 + v) * ldb] = X[i * LDX + v];
+    }
+  } else {
+    for (int idx = tid; idx < LB * NV; idx += 256) {
+      const int v = idx % NV, i = idx / NV;
+      if (i < nb && v < nv) B[(v0 + v) + (int64_t)i * ldb] = X[i * LDX + v];
+    }
+  }
+}
+
 // ---- DRAFT (round 2, compiled but not yet run on hardware; opt-in with B200BLAS_TRSM=inv) --------------------------------
 // Inverses of all diagonal leaf blocks of T = op(A) in ONE launch (one CTA per block), so that a leaf of the solve is a
 // product X_b = inv(T_bb) * B_b on the tensor-pipe kernels instead of 8256 FMA + LDS per right-hand side on the SIMT
@@ -290,6 +398,11 @@ __global__ void __launch_bounds__(256) symm_expand_kernel(int uplo, int herm, in
 template <typename T> struct LeafOrder { static constexpr int NB = 32; static constexpr int NSUB = 4; };
 template <> struct LeafOrder<double2> { static constexpr int NB = 16; static constexpr int NSUB = 4; };
 
+// right-hand sides per CTA of tri_block_solve_kernel: S (LB x (LB+1)) + X (LB x (NV+1)) must fit 227 KB of shared memory
+template <typename T> struct BlockSolve { static constexpr int NV = 64; };          // double / complex<float>: 132 + 66.5 KB
+template <> struct BlockSolve<float> { static constexpr int NV = 64; };
+template <> struct BlockSolve<double2> { static constexpr int NV = 64; };           // LB = 64: 66.5 + 66.5 KB
+
 template <typename T>
 T scalar_of(const double a[2]) {
   if constexpr (sizeof(T) == sizeof(typename Sc<T>::real)) return (T)a[0];
@@ -312,6 +425,17 @@ int launch_leaf(const TriProblem& p, bool s_lower, int64_t d0, int nb, cudaStrea
     B200_CUDA_TRY(run_gemm_device(g, s, B200BLAS_AUTO));
     return (int)cudaMemcpy2DAsync(B, (size_t)p.ldb * sizeof(T), p.Xtmp, (size_t)g.ldc * sizeof(T), (size_t)g.m * sizeof(T), (size_t)g.n,
                                   cudaMemcpyDeviceToDevice, s);
+  }
+  if constexpr (SOLVE) {
+    static const bool block_solve = [] { const char* e = getenv("B200BLAS_TRSM_LEAF"); return !(e && e[0] == 'v'); }();   // "vector": the kernel above
+    if (s_lower && block_solve) {
+      constexpr int NV = BlockSolve<T>::NV;
+      constexpr size_t bsmem = ((size_t)LB * (LB + 1) + (size_t)LB * (NV + 1)) * sizeof(T);
+      B200_SET_MAX_DYN_SMEM_ONCE((tri_block_solve_kernel<T, LB, NV>), bsmem);
+      tri_block_solve_kernel<T, LB, NV><<<(unsigned)((nrhs + NV - 1) / NV), 256, bsmem, s>>>(p.left, p.op, p.uplo, p.unit, nb, nrhs, A, p.lda, B, p.ldb);
+      count_launch();
+      return (int)cudaGetLastError();
+    }
   }
   const unsigned grid = (unsigned)((nrhs + LEAF_THREADS - 1) / LEAF_THREADS);
   constexpr size_t smem = (size_t)LB * LB * sizeof(T);
@@ -482,6 +606,10 @@ int launch_trtri_diag(const TriProblem& p, void* V, cudaStream_t s) {
 }
 bool trsm_substitution_forced() {
   static const bool v = [] { const char* e = getenv("B200BLAS_TRSM"); return e && e[0] == 's'; }();
+  return v;
+}
+bool trsm_inverse_forced() {
+  static const bool v = [] { const char* e = getenv("B200BLAS_TRSM"); return e && e[0] == 'i'; }();
   return v;
 }
 int launch_trmm(const TriProblem& p, cudaStream_t s) { return dispatch_tri<false>(p, s); }
