@@ -920,6 +920,36 @@ int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, c
   return 0;
 }
 
+// Tensor contraction seam (unsupported/Eigen/CXX11/src/Tensor/TensorContractionCuda.h:1320-1390): the GpuDevice
+// evaluator reduces every contraction to out(m x n, column-major) = lhs(m x k) * rhs(k x n) over strided views of device
+// memory and then launches its own SIMT kernels.  When both views are matrices in the BLAS sense (one unit stride each) this
+// entry runs the product on the sm_100a kernels instead; otherwise it returns 1 and the caller keeps its own path.
+int b200blas_contract_dev(int type, int64_t m, int64_t n, int64_t k, const void* lhs, int64_t lhs_row_stride, int64_t lhs_col_stride,
+                          const void* rhs, int64_t rhs_row_stride, int64_t rhs_col_stride, void* out, int64_t ldo, void* stream) {
+  if (type < 0 || type > 3 || m < 0 || n < 0 || k < 0 || !out) return -1;
+  if (m == 0 || n == 0) return 0;
+  if (m > INT_MAX || n > INT_MAX || k > INT_MAX || !lhs || !rhs) return 1;
+  char ta, tb;
+  int64_t lda, ldb;
+  // lhs(i, kk) = lhs[i * row_stride + kk * col_stride]
+  if (lhs_row_stride == 1 || m == 1) { ta = 'N'; lda = std::max<int64_t>(k == 1 ? m : lhs_col_stride, std::max<int64_t>(m, 1)); if (k > 1 && lhs_col_stride < m) return 1; }
+  else if (lhs_col_stride == 1 || k == 1) { ta = 'T'; lda = std::max<int64_t>(lhs_row_stride, std::max<int64_t>(k, 1)); if (lhs_row_stride < k) return 1; }
+  else return 1;
+  // rhs(kk, j) = rhs[kk * row_stride + j * col_stride]
+  if (rhs_row_stride == 1 || k == 1) { tb = 'N'; ldb = std::max<int64_t>(n == 1 ? k : rhs_col_stride, std::max<int64_t>(k, 1)); if (n > 1 && rhs_col_stride < k) return 1; }
+  else if (rhs_col_stride == 1 || n == 1) { tb = 'T'; ldb = std::max<int64_t>(rhs_row_stride, std::max<int64_t>(n, 1)); if (rhs_row_stride < n) return 1; }
+  else return 1;
+  const double one[2] = {1.0, 0.0}, zero[2] = {0.0, 0.0};
+  float onef[2] = {1.f, 0.f}, zerof[2] = {0.f, 0.f};
+  const bool sp = type == TY_S || type == TY_C;
+  const int r = b200blas_gemm_dev(type, ta, tb, (int)m, (int)n, (int)k, sp ? (const void*)onef : (const void*)one, lhs, lda, rhs, ldb,
+                                  sp ? (const void*)zerof : (const void*)zero, out, ldo, stream, B200BLAS_AUTO);
+  if (log_enabled())
+    fprintf(stderr, "[b200blas] contract %c%c m=%lld n=%lld k=%lld operands=device variant=%s%s\n", ta, tb, (long long)m, (long long)n,
+            (long long)k, t_variant, r ? " FAILED" : "");
+  return r == 0 ? 0 : -1;
+}
+
 int b200blas_version(void) { return 100; }
 int b200blas_device_ok(void) {
   int dev = 0;

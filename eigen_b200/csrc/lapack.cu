@@ -182,13 +182,30 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
   extern __shared__ __align__(16) unsigned char blk_smem[];
   T* S = reinterpret_cast<T*>(blk_smem);   // S[i * LDS + j], i >= j
   __shared__ T colbuf[3][64];
+  __shared__ R roots[2][32];
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < NBL * NBL; idx += 256) {
-    int i, j;
-    if (upper) { j = idx % NBL; i = idx / NBL; } else { i = idx % NBL; j = idx / NBL; }   // coalesced either way
-    T v = (i == j) ? sc_one<T>() : Sc<T>::zero();
-    if (i < d && j <= i) v = upper ? Sc<T>::conj(A[j + (int64_t)i * lda]) : A[i + (int64_t)j * lda];
-    S[i * LDS + j] = v;
+  {
+    // all loads of a batch are issued before any is consumed (a load-per-iteration loop costs one DRAM latency per element:
+    // 64 x 700 cycles for this block)
+    constexpr int BATCH = 16;
+    for (int base = 0; base < NBL * NBL; base += 256 * BATCH) {
+      T vals[BATCH];
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * 256 + tid;
+        int i, j;
+        if (upper) { j = idx % NBL; i = idx / NBL; } else { i = idx % NBL; j = idx / NBL; }   // coalesced either way
+        vals[q] = (i == j) ? sc_one<T>() : Sc<T>::zero();
+        if (idx < NBL * NBL && i < d && j <= i) vals[q] = upper ? Sc<T>::conj(A[j + (int64_t)i * lda]) : A[i + (int64_t)j * lda];
+      }
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * 256 + tid;
+        int i, j;
+        if (upper) { j = idx % NBL; i = idx / NBL; } else { i = idx % NBL; j = idx / NBL; }
+        if (idx < NBL * NBL) S[i * LDS + j] = vals[q];
+      }
+    }
   }
   __syncthreads();
   bool ok = true;   // uniform over the CTA
@@ -208,15 +225,17 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
     __syncthreads();
     // Critical path of a column = barrier -> pivot x -> 1/x -> update of the NEXT column's entry -> publish -> barrier:
     // the update uses w = a(i,k) / x against the RAW column (a(i,j) -= w * conj(a(j,k)), the same product as
-    // L(i,k) conj(L(j,k))), so neither the square root nor the scaled column is on that path; the roots, the stored L entries
-    // and the other 30 updates of the row are issued after the barrier, under the next column's latency.
+    // L(i,k) conj(L(j,k))), so no square root is on that path -- the column is stored unscaled, the pivots are kept, and
+    // the 32 roots are taken in parallel after the loop (one thread each), followed by one scaling pass over the panel.
     R x = sc_real<T>(colbuf[0][0]);
-    R inv_x = (R)1 / x;
+    R inv_x = fast_rcp(x);
+    int ncols = 32;   // columns of this panel that were factored (all of them unless a pivot failed)
 #pragma unroll 1
     for (int k = 0; k < 32; ++k) {
       if (x <= (R)0) {   // a NaN pivot continues, as in the reference (LLT.h:316-317)
         if (tid == 0) atomicMin(info, (int)(d0 + c0 + k + 1));
         ok = false;
+        ncols = k;
         break;
       }
       const T* col = colbuf[k % 3];
@@ -230,11 +249,9 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
         if (t < 32 && t > k) colbuf[(k + 1) % 3][t] = v1;
         __syncthreads();
         xn = sc_real<T>(colbuf[(k + 1) % 3][k + 1]);
-        inv_xn = (R)1 / xn;
+        inv_xn = fast_rcp(xn);
       }
-      R l, rl;
-      pivot_roots(x, l, rl);
-      if (rowact && t >= k) S[(c0 + t) * LDS + c0 + k] = (t == k) ? sc_from_real<T>(l) : sc_scale<T>(a0, rl);   // L(c0 + t, c0 + k)
+      if (rowact && t >= k) S[(c0 + t) * LDS + c0 + k] = (t == k) ? sc_from_real<T>(x) : a0;   // unscaled; the diagonal keeps the pivot
       a[0] = v1;
 #pragma unroll
       for (int j = 2; j < 32; ++j) {
@@ -244,6 +261,18 @@ __global__ void __launch_bounds__(256) potf2_block_kernel(int upper, int d, int6
       }
       a[31] = Sc<T>::zero();
       x = xn; inv_x = inv_xn;
+    }
+    __syncthreads();
+    // roots of the panel's pivots (one thread each), then L(i, k) = a(i, k) / sqrt(x_k) for the whole panel
+    if (tid < ncols) {
+      R l, rl;
+      pivot_roots(sc_real<T>(S[(c0 + tid) * LDS + c0 + tid]), l, rl);
+      roots[0][tid] = l; roots[1][tid] = rl;
+    }
+    __syncthreads();
+    if (rowact) {
+      T* srow = S + (c0 + t) * LDS + c0;
+      for (int k = 0; k < ncols && k <= t; ++k) srow[k] = (k == t) ? sc_from_real<T>(roots[0][k]) : sc_scale<T>(srow[k], roots[1][k]);
     }
     __syncthreads();
     const int c1 = c0 + 32;
@@ -739,7 +768,7 @@ __device__ __forceinline__ void static_for(F&& f) {
 
 template <typename T, int NBP>
 struct RegPanelTables {
-  double score[2][16];
+  unsigned long long score[2][16];   // score_key of every CTA's candidate
   int row[2][16];
   T vals[2][16][NBP];
   T rowk[2][NBP];
@@ -755,15 +784,20 @@ struct RegPanelTables {
 // of its stall samples in the barrier's fence).  The interchange of the already-final L part of rows k and pivot (columns
 // < k) is done on the Lbuf columns, through distributed shared memory, by one warp.  All reductions are shuffle trees
 // (max of the scores, then the smallest row among the lanes that hold the maximum = maxCoeff's "first").
-__device__ __forceinline__ void argmax_tree(double& best, int& brow) {   // warp-wide: largest score, smallest row on ties
-  double m = best;
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const double o = __shfl_xor_sync(0xffffffffu, m, off);
-    m = o > m ? o : m;
-  }
-  brow = (int)__reduce_min_sync(0xffffffffu, (unsigned)((best == m) ? brow : INT_MAX));
-  best = m;
+// A pivot candidate is (key, row): key = bit pattern of the score |a| plus one (doubles >= 0 order like their bit patterns;
+// 0 = no candidate: no row, or a NaN score, which never compares greater in maxCoeff).  Warp-wide arg-max = three REDUX
+// instructions (max of the high words, max of the low words among the lanes that hold it, min of the rows among the lanes
+// that hold both) instead of a five-level shuffle tree on 64-bit values.
+__device__ __forceinline__ unsigned long long score_key(double sc) {
+  return sc >= 0.0 ? (unsigned long long)__double_as_longlong(sc) + 1ull : 0ull;   // false for NaN
+}
+__device__ __forceinline__ void argmax_tree(unsigned long long& key, int& row) {
+  const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+  row = (int)__reduce_min_sync(0xffffffffu, (unsigned)((key == m) ? row : INT_MAX));
+  key = m;
 }
 
 template <typename T, int NBP, int RPT, int THREADS>
@@ -777,7 +811,7 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
   __shared__ RegPanelTables<T, NBP> tab;
   __shared__ T Ubuf[NBP][NBP];                // CTA 0: Ubuf[k][j] = U(k, k + j)
   __shared__ int ipiv_s[NBP];                 // CTA 0
-  __shared__ double wbest[NW];
+  __shared__ unsigned long long wbest[NW];
   __shared__ int wrow[NW];
   __shared__ T myrow[NBP], mykrow[NBP];
   cg::cluster_group cluster = cg::this_cluster();
@@ -797,26 +831,26 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
   for (int k = 0; k < steps; ++k) {
     const int par = k & 1;
     // 1. candidate of this thread -> warp: largest |a(r,k)| among rows >= k, smallest row on ties (maxCoeff keeps the first)
-    double best = -1.0;
+    unsigned long long best = 0ull;
     int brow = INT_MAX;
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       if (rq[q] >= k && rq[q] < mrows) {
-        const double sc = sc_score<T>(a[q][0]);
-        if (sc > best) { best = sc; brow = rq[q]; }   // rq[0] < rq[1]: the first row wins a tie
+        const unsigned long long sk = score_key(sc_score<T>(a[q][0]));
+        if (sk > best) { best = sk; brow = rq[q]; }   // rq[0] < rq[1]: the first row wins a tie
       }
     }
     argmax_tree(best, brow);
     if (lane == 0) { wbest[warp] = best; wrow[warp] = brow; }
     __syncthreads();
     // 2. warp results -> the CTA's candidate (every warp runs the same tree); its owner and the owner of row k publish their rows
-    double cb = lane < NW ? wbest[lane] : -1.0;
+    unsigned long long cb = lane < NW ? wbest[lane] : 0ull;
     int crow = lane < NW ? wrow[lane] : INT_MAX;
     argmax_tree(cb, crow);
     const int krow_cta = k / RT;   // the CTA that owns row k
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-      if (cb >= 0.0 && rq[q] == crow) {
+      if (cb != 0ull && rq[q] == crow) {
 #pragma unroll
         for (int c = 0; c < NBP; ++c) myrow[c] = a[q][c];
       }
@@ -829,7 +863,7 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
     for (int idx = tid; idx < CL * NBP; idx += THREADS) {
       const int peer = idx / NBP, c = idx % NBP;
       RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, peer);
-      if (cb >= 0.0) rt->vals[par][cta][c] = myrow[c];
+      if (cb != 0ull) rt->vals[par][cta][c] = myrow[c];
       if (cta == krow_cta) rt->rowk[par][c] = mykrow[c];
     }
     if (tid < CL) {
@@ -839,15 +873,15 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
     }
     cluster.sync();   // release / acquire at cluster scope: the remote stores of this column are visible
     // 3. identical reduction of the CL candidates in every warp
-    double gb = -1.0;
+    unsigned long long gb = 0ull;
     int grow = INT_MAX;
     if (lane < CL) {
-      const double s2 = tab.score[par][lane];
-      if (s2 >= 0.0) { gb = s2; grow = tab.row[par][lane]; }
+      gb = tab.score[par][lane];
+      if (gb != 0ull) grow = tab.row[par][lane];
     }
     const int my_row = grow;
     argmax_tree(gb, grow);
-    const bool nonzero = gb > 0.0;        // zero (or all-NaN) pivot column: recorded and skipped (PartialPivLU.h:396-401)
+    const bool nonzero = gb > 1ull;       // key 1 = score 0: zero (or, key 0, all-NaN) pivot column: recorded and skipped (PartialPivLU.h:396-401)
     const int gw = __ffs(__ballot_sync(0xffffffffu, my_row == grow && grow != INT_MAX)) - 1;   // the CTA that holds the winner
     const int piv = (nonzero && gw >= 0) ? grow : k;
     const bool have = nonzero && gw >= 0;
@@ -869,7 +903,7 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
       lp = cluster.map_shared_rank(Lbuf, piv / RT) + (size_t)lane * RT + piv % RT;
       t1 = *lk; t2 = *lp;
     }
-    const T inv_pv = have ? sc_recip<T>(urow[0]) : Sc<T>::zero();
+    const T inv_pv = have ? sc_fast_recip<T>(urow[0]) : Sc<T>::zero();
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       // 4. interchange rows k and piv (PartialPivLU.h:384-388): the owner of position piv takes over the old row k

@@ -65,6 +65,31 @@ template <> __device__ __forceinline__ double2 sc_recip<double2>(double2 a) {
   if (fabs(a.x) >= fabs(a.y)) { const double r = a.y / a.x, d = a.x + a.y * r; return make_double2(1.0 / d, -r / d); }
   const double r = a.x / a.y, d = a.x * r + a.y; return make_double2(r / d, -1.0 / d);
 }
+// Reciprocal for latency-critical pivots (the leaf kernels of ?potrf_ / ?getrf_ wait on it once per column): the IEEE double
+// division is a ~30-instruction dependent sequence (350+ cycles of "wait" stalls in ncu); a float MUFU.RCP seed refined by two
+// Newton steps in double is ~8 dependent instructions and accurate to about one ulp.  Arguments outside the float range
+// (and 0, Inf, NaN) take the IEEE path.
+__device__ __forceinline__ double fast_rcp(double x) {
+  const float xf = (float)x;
+  if (!(fabsf(xf) > 1e-30f && fabsf(xf) < 1e30f)) return 1.0 / x;
+  double r = (double)__frcp_rn(xf);
+  double e = ::fma(-x, r, 1.0);
+  r = ::fma(r, e, r);
+  e = ::fma(-x, r, 1.0);
+  return ::fma(r, e, r);
+}
+__device__ __forceinline__ float fast_rcp(float x) { return __frcp_rn(x); }
+template <typename T> __device__ __forceinline__ T sc_fast_recip(T a);
+template <> __device__ __forceinline__ float sc_fast_recip<float>(float a) { return fast_rcp(a); }
+template <> __device__ __forceinline__ double sc_fast_recip<double>(double a) { return fast_rcp(a); }
+template <> __device__ __forceinline__ float2 sc_fast_recip<float2>(float2 a) {   // Smith's algorithm: no spurious overflow
+  if (fabsf(a.x) >= fabsf(a.y)) { const float r = a.y * fast_rcp(a.x), d = fast_rcp(a.x + a.y * r); return make_float2(d, -r * d); }
+  const float r = a.x * fast_rcp(a.y), d = fast_rcp(a.x * r + a.y); return make_float2(r * d, -d);
+}
+template <> __device__ __forceinline__ double2 sc_fast_recip<double2>(double2 a) {
+  if (fabs(a.x) >= fabs(a.y)) { const double r = a.y * fast_rcp(a.x), d = fast_rcp(a.x + a.y * r); return make_double2(d, -r * d); }
+  const double r = a.x * fast_rcp(a.y), d = fast_rcp(a.x * r + a.y); return make_double2(r * d, -d);
+}
 template <typename T> __device__ __forceinline__ T sc_one() { return Sc<T>::make(1.0, 0.0); }
 // c -= a * b
 template <typename T> __device__ __forceinline__ void sc_fnma(T& c, T a, T b);

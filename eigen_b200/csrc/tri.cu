@@ -182,29 +182,53 @@ tri_block_solve_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrh
   T* X = S + LB * LDSS;                    // X[i * LDX + v]
   const int tid = threadIdx.x;
   const bool swap = left ? (op != OP_N) : (op == OP_N);
-  for (int idx = tid; idx < LB * LB; idx += 256) {
-    const int r = idx % LB, c = idx / LB;   // element of A (coalesced along r)
-    const bool referenced = r < nb && c < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
-    T v = (r == c) ? sc_one<T>() : Sc<T>::zero();
-    if (referenced) {
-      v = A[r + (int64_t)c * lda];
-      if (op == OP_C) v = Sc<T>::conj(v);
-      if (r == c) v = sc_recip<T>(v);
-    }
-    const int i = swap ? c : r, j = swap ? r : c;
-    S[i * LDSS + j] = v;
-  }
   const int64_t v0 = (int64_t)blockIdx.x * NV;
   const int nv = (int)min((int64_t)NV, nrhs - v0);
-  if (left) {
-    for (int idx = tid; idx < LB * NV; idx += 256) {
-      const int i = idx % LB, v = idx / LB;
-      X[i * LDX + v] = (i < nb && v < nv) ? B[i + (v0 + v) * ldb] : Sc<T>::zero();
+  {
+    // all loads of a batch are issued before any is consumed (a load-per-iteration loop costs one DRAM latency per element)
+    constexpr int BATCH = 16;
+    for (int base = 0; base < LB * LB; base += 256 * BATCH) {
+      T vals[BATCH];
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * 256 + tid;
+        const int r = idx % LB, c = idx / LB;   // element of A (coalesced along r)
+        const bool referenced = idx < LB * LB && r < nb && c < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
+        vals[q] = (r == c) ? sc_one<T>() : Sc<T>::zero();
+        if (referenced) vals[q] = A[r + (int64_t)c * lda];
+      }
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * 256 + tid;
+        if (idx >= LB * LB) continue;
+        const int r = idx % LB, c = idx / LB;
+        const bool referenced = r < nb && c < nb && ((r == c) ? !unit : (uplo == UPLO_UPPER ? r < c : r > c));
+        T v = vals[q];
+        if (referenced) {
+          if (op == OP_C) v = Sc<T>::conj(v);
+          if (r == c) v = sc_recip<T>(v);
+        }
+        const int i = swap ? c : r, j = swap ? r : c;
+        S[i * LDSS + j] = v;
+      }
     }
-  } else {
-    for (int idx = tid; idx < LB * NV; idx += 256) {
-      const int v = idx % NV, i = idx / NV;
-      X[i * LDX + v] = (i < nb && v < nv) ? B[(v0 + v) + (int64_t)i * ldb] : Sc<T>::zero();
+    for (int base = 0; base < LB * NV; base += 256 * BATCH) {
+      T vals[BATCH];
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * 256 + tid;
+        int i, v;
+        if (left) { i = idx % LB; v = idx / LB; } else { v = idx % NV; i = idx / NV; }
+        vals[q] = Sc<T>::zero();
+        if (idx < LB * NV && i < nb && v < nv) vals[q] = left ? B[i + (v0 + v) * ldb] : B[(v0 + v) + (int64_t)i * ldb];
+      }
+#pragma unroll
+      for (int q = 0; q < BATCH; ++q) {
+        const int idx = base + q * 256 + tid;
+        int i, v;
+        if (left) { i = idx % LB; v = idx / LB; } else { v = idx % NV; i = idx / NV; }
+        if (idx < LB * NV) X[i * LDX + v] = vals[q];
+      }
     }
   }
   __syncthreads();

@@ -151,6 +151,15 @@ int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, c
                       int64_t lda, const void* dB, int64_t ldb, const void* beta, void* dC, int64_t ldc,
                       void* stream, int variant);
 
+/* Tensor contraction seam (replaces the LaunchKernels step of
+ * unsupported/Eigen/CXX11/src/Tensor/TensorContractionCuda.h:1320-1390): out (m x n, column-major, leading dimension ldo)
+ * = lhs * rhs, lhs(i, kk) = lhs[i * lhs_row_stride + kk * lhs_col_stride], rhs(kk, j) = rhs[kk * rhs_row_stride + j *
+ * rhs_col_stride] (strides in elements, device pointers).  Returns 0 = done on `stream`, 1 = the views are not BLAS matrices
+ * (no unit stride): the caller keeps its own path, -1 = error.  include/b200blas_eigen_tensor.h is the C++ glue the evaluator
+ * calls. */
+int b200blas_contract_dev(int type, int64_t m, int64_t n, int64_t k, const void* lhs, int64_t lhs_row_stride, int64_t lhs_col_stride,
+                          const void* rhs, int64_t rhs_row_stride, int64_t rhs_col_stride, void* out, int64_t ldo, void* stream);
+
 /* introspection used by tests and bench.py */
 int b200blas_version(void);
 int b200blas_device_ok(void);                 /* 1 if the current device is sm_100 and the kernels loaded */

@@ -51,3 +51,21 @@ def test_eigen_tests_pass_with_the_multi_gpu_partitioner(name):
     """the reference's own tests, unmodified, with B200BLAS_NGPUS=8 -- every product is cut into the
     2x4 grid inside dgemm_ (Parallelizer.h:85-157 is what the reference does at this point)."""
     _run(name, "auto", 777, ngpus=8)
+
+
+def test_eigen_tensor_contraction_test_runs_on_the_gpu_library():
+    """the reference's own unsupported/test/cxx11_tensor_contract_cuda.cu (GpuDevice contractions, ColMajor and
+    RowMajor, the m / k / n size sweeps and the scalar case), compiled unmodified against the Tensor headers with the
+    five-line binding of INTEGRATION.md section 4 (oracle/patch_tensor_contraction.py).  The test compares every result with
+    Eigen's CPU contraction itself; B200BLAS_LOG shows that the products really ran on our kernels."""
+    exe = os.path.join(BIN, "eigen_test_tensor_contract_cuda")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/eigen_test_tensor_contract_cuda not built (make -C oracle tensor_test needs /root/reference)")
+    env = dict(os.environ, B200BLAS_LOG="1")
+    p = subprocess.run([exe, "r1", "s99"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900, text=True)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert "mismatch detected" not in p.stdout
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("[b200blas] contract")]
+    assert len(lines) >= 50, "the contractions did not go through b200blas_contract_dev:\n" + p.stdout[-2000:]
+    assert not any("FAILED" in ln for ln in lines)
+    assert any("tf32x3" in ln for ln in lines) and any("simt" in ln for ln in lines), "both the tensor and the SIMT variant should appear"
