@@ -384,7 +384,12 @@ int potrf_blocked(const PotrfProblem& p, cudaStream_t s) {
   const int64_t n = p.n;
   constexpr size_t smem = (size_t)NBL * (NBL + 1) * sizeof(T);
   B200_SET_MAX_DYN_SMEM_ONCE((potf2_block_kernel<T, NBL>), smem);
-  const bool look = lookahead_enabled() && n > 4 * NBL;
+  // Two-level blocking: the one-CTA block kernel factors NBL columns at a time, but the bulk update uses the last NBO columns as
+  // its k dimension.  B200BLAS_POTRF_NB=<multiple of NBL> sets NBO (default NBL: rank-128 updates; 2 * NBL halves the number
+  // of passes over the trailing matrix -- a rank-256 update runs at 0.87 of the DMMA pipe, a rank-128 one at ~0.75).
+  static const int nbo_env = [] { const char* e = getenv("B200BLAS_POTRF_NB"); return e ? atoi(e) : 0; }();
+  const int64_t NBO = (nbo_env >= NBL && nbo_env % NBL == 0 && n >= 8 * (int64_t)nbo_env) ? nbo_env : NBL;
+  const bool look = lookahead_enabled() && n > 4 * NBO;
   cudaStream_t sp = s;
   LookAhead& la = t_look;
   if (look) {
@@ -394,19 +399,26 @@ int potrf_blocked(const PotrfProblem& p, cudaStream_t s) {
     B200_CUDA_TRY(cudaStreamWaitEvent(sp, la.e_in, 0));
   }
   bool rest_pending = false;
-  for (int64_t j = 0; j < n; j += NBL) {
-    const int64_t jb = std::min<int64_t>(NBL, n - j), n2 = n - j - jb;
-    potf2_block_kernel<T, NBL><<<1, 256, smem, sp>>>(upper ? 1 : 0, (int)jb, j, A + j + j * p.lda, p.lda, p.dinfo);
-    count_launch();
-    B200_CUDA_TRY(cudaGetLastError());
+  for (int64_t j = 0; j < n; j += NBO) {
+    const int64_t jb = std::min<int64_t>(NBO, n - j), n2 = n - j - jb;
+    // panel [j, j + jb): block by block -- factor the diagonal block, solve the rows below it, update the rest of the panel
+    for (int64_t jj = j; jj < j + jb; jj += NBL) {
+      const int64_t jbb = std::min<int64_t>(NBL, j + jb - jj), below = n - jj - jbb;
+      potf2_block_kernel<T, NBL><<<1, 256, smem, sp>>>(upper ? 1 : 0, (int)jbb, jj, A + jj + jj * p.lda, p.lda, p.dinfo);
+      count_launch();
+      B200_CUDA_TRY(cudaGetLastError());
+      if (below <= 0) break;
+      TriProblem t;   // A21 := A21 * L11^-H  /  A12 := U11^-H * A12   (LLT.h:356)
+      t.type = p.type; t.uplo = p.uplo; t.op = OP_C; t.unit = 0; t.alpha[0] = 1.0; t.alpha[1] = 0.0;
+      t.A = A + jj + jj * p.lda; t.lda = p.lda; t.ldb = p.lda;
+      if (!upper) { t.left = 0; t.m = below; t.n = jbb; t.B = A + (jj + jbb) + jj * p.lda; }
+      else { t.left = 1; t.m = jbb; t.n = below; t.B = A + jj + (jj + jbb) * p.lda; }
+      B200_CUDA_TRY(launch_trsm(t, sp));
+      const int64_t rp = jj + jbb, ncp = j + jb - rp;   // rest of the panel: columns [rp, j + jb), rows rp..
+      if (ncp > 0) B200_CUDA_TRY(potrf_update<T>(p, jj, jbb, rp, n - rp, rp, ncp, sp));
+    }
     if (n2 <= 0) break;
-    TriProblem t;   // A21 := A21 * L11^-H  /  A12 := U11^-H * A12   (LLT.h:356)
-    t.type = p.type; t.uplo = p.uplo; t.op = OP_C; t.unit = 0; t.alpha[0] = 1.0; t.alpha[1] = 0.0;
-    t.A = A + j + j * p.lda; t.lda = p.lda; t.ldb = p.lda;
-    if (!upper) { t.left = 0; t.m = n2; t.n = jb; t.B = A + (j + jb) + j * p.lda; }
-    else { t.left = 1; t.m = jb; t.n = n2; t.B = A + j + (j + jb) * p.lda; }
-    B200_CUDA_TRY(launch_trsm(t, sp));
-    const int64_t r1 = j + jb, nb2 = std::min<int64_t>(NBL, n2), r2 = r1 + nb2, n3 = n - r2;
+    const int64_t r1 = j + jb, nb2 = std::min<int64_t>(NBO, n2), r2 = r1 + nb2, n3 = n - r2;
     if (look) {
       B200_CUDA_TRY(cudaEventRecord(la.e_panel, sp));
       if (rest_pending) B200_CUDA_TRY(cudaStreamWaitEvent(sp, la.e_rest, 0));   // the previous bulk update also touched the next block column
