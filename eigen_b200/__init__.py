@@ -26,7 +26,7 @@ EXPORTS = ["sgemm_", "dgemm_", "cgemm_", "zgemm_", "ssyrk_", "dsyrk_", "csyrk_",
            "b200blas_device_ok", "b200blas_last_error", "b200blas_last_variant", "b200blas_kernel_launches",
            "b200blas_set_variant", "b200blas_last_transfer", "b200blas_release", "b200blas_pipe_peak",
            "b200blas_set_devices", "b200blas_get_devices", "b200blas_set_grid", "b200blas_host_register",
-           "b200blas_host_unregister", "b200blas_multi_plan"]
+           "b200blas_host_unregister", "b200blas_multi_plan", "b200blas_contract_dev"]
 
 
 class Region(C.Structure):
@@ -121,6 +121,7 @@ def lib():
     L.b200blas_set_grid.argtypes = [i, i]
     L.b200blas_host_register.argtypes = [vp, C.c_uint64]
     L.b200blas_host_unregister.argtypes = [vp]
+    L.b200blas_contract_dev.argtypes = [i, C.c_int64, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int64, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp]
     L.b200blas_multi_plan.argtypes = [i, C.c_char, C.c_char, C.c_int64, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                       C.c_int64, C.c_int64, C.c_int64, i, i, i, i, C.POINTER(PlanInfo), C.POINTER(Step), i]
     _lib = L

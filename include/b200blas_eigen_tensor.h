@@ -3,8 +3,7 @@
  * Reference seam: TensorEvaluator<const TensorContractionOp<...>, GpuDevice>::evalTyped
  * (unsupported/Eigen/CXX11/src/Tensor/TensorContractionCuda.h:1320-1390) builds LhsMapper / RhsMapper over the operands'
  * strides and launches EigenContractionKernel / EigenFloatContractionKernel.  With -DEIGEN_USE_B200BLAS the evaluator first
- * offers the product to this header (the five-line patch is oracle/patch_tensor_contraction.py, shown in INTEGRATION.md
- * section 4); contractions whose three index groups (left free, contracted, right free) are each contiguous-mergeable --
+ * offers the product to this header (the five-line binding is shown in INTEGRATION.md section 5); contractions whose three index groups (left free, contracted, right free) are each contiguous-mergeable --
  * every matrix product and every contraction of leading / trailing index groups -- run on the sm_100a GEMM kernels, anything
  * else falls through to the reference's own kernels unchanged.  Header only; needs nothing but b200blas.h. */
 #ifndef B200BLAS_EIGEN_TENSOR_H
