@@ -385,10 +385,13 @@ int potrf_blocked(const PotrfProblem& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)NBL * (NBL + 1) * sizeof(T);
   B200_SET_MAX_DYN_SMEM_ONCE((potf2_block_kernel<T, NBL>), smem);
   // Two-level blocking: the one-CTA block kernel factors NBL columns at a time, but the bulk update uses the last NBO columns as
-  // its k dimension.  B200BLAS_POTRF_NB=<multiple of NBL> sets NBO (default NBL: rank-128 updates; 2 * NBL halves the number
-  // of passes over the trailing matrix -- a rank-256 update runs at 0.87 of the DMMA pipe, a rank-128 one at ~0.75).
+  // its k dimension: 2 * NBL halves the number of passes over the trailing matrix (a rank-256 update runs at 0.87 of the
+  // DMMA pipe, a rank-128 one at ~0.75).  Measured on B200 (profiles/bench_r02/potrf_two_level_pass9.txt), NBO = 128 / 256 /
+  // 512: dpotrf 8192 14.84 / 15.06 / 14.08, dpotrf 16384 23.33 / 25.20 / 25.64, spotrf 8192 16.41 / 17.23 / 17.52 TFLOP/s.
+  // B200BLAS_POTRF_NB=<multiple of NBL> overrides.
   static const int nbo_env = [] { const char* e = getenv("B200BLAS_POTRF_NB"); return e ? atoi(e) : 0; }();
-  const int64_t NBO = (nbo_env >= NBL && nbo_env % NBL == 0 && n >= 8 * (int64_t)nbo_env) ? nbo_env : NBL;
+  const int64_t nbo_want = nbo_env > 0 ? nbo_env : 2 * NBL;
+  const int64_t NBO = (nbo_want >= NBL && nbo_want % NBL == 0 && n >= 8 * nbo_want) ? nbo_want : NBL;
   const bool look = lookahead_enabled() && n > 4 * NBO;
   cudaStream_t sp = s;
   LookAhead& la = t_look;
@@ -1063,8 +1066,45 @@ __global__ void __launch_bounds__(256) perm_apply_fused_kernel(int ns, int64_t n
   }
 }
 
+// Up to 128 interchanges: no separate permutation pass at all.  Only the <= 2 ns rows {k} and {piv_k} change; every CTA
+// finds the source of each of them itself by undoing the interchanges in reverse order (one thread per destination,
+// ns steps of two compares on the pivot list in shared memory), then moves its columns: read every source, __syncthreads,
+// write every destination.
+constexpr int DIRECT_NS = 128;
+template <typename T>
+__global__ void __launch_bounds__(256) perm_apply_direct_kernel(const int* __restrict__ ipiv, int64_t k0, int ns, int mrows, int64_t ncols,
+                                                                T* __restrict__ A, int64_t lda) {
+  __shared__ int piv[DIRECT_NS];
+  const int tid = threadIdx.x;
+  if (tid < ns) {
+    const int pv = ipiv[k0 + tid] - 1 - (int)k0;
+    piv[tid] = (pv >= 0 && pv < mrows) ? pv : tid;
+  }
+  __syncthreads();
+  // destination of this thread: top rows 0 .. ns-1 (threads 0 .. ns-1), far rows piv_t >= ns (threads ns .. 2 ns - 1)
+  int dst = -1;
+  if (tid < ns) dst = tid;
+  else if (tid < 2 * ns && piv[tid - ns] >= ns) dst = piv[tid - ns];
+  int src = dst;
+  if (dst >= 0) {
+    for (int k = ns - 1; k >= 0; --k) {
+      const int pk = piv[k];
+      if (src == k) src = pk; else if (src == pk) src = k;
+    }
+  }
+  const bool moves = dst >= 0 && src != dst;
+  for (int64_t c = blockIdx.x; c < ncols; c += gridDim.x) {
+    T* col = A + c * lda;
+    T v = Sc<T>::zero();
+    if (moves) v = col[src];
+    __syncthreads();
+    if (moves) col[dst] = v;
+  }
+}
+
 // the permutation of the interchanges ipiv[k0 .. k0+ns) (rows k0 .. m) into cx's lists
 inline int build_perm(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t ns, cudaStream_t s) {
+  if (ns <= DIRECT_NS) return 0;   // perm_apply_direct_kernel needs no lists
   const int64_t mrows = p.m - k0;
   if ((size_t)mrows * sizeof(int) + 2048 <= cx.max_dyn_smem) {
     perm_build_kernel<<<1, 1024, (size_t)mrows * sizeof(int), s>>>(p.dipiv, k0, (int)ns, (int)mrows, cx.src_top, cx.disp_dst, cx.disp_src, cx.disp_count);
@@ -1079,6 +1119,12 @@ template <typename T>
 int apply_perm(const GetrfProblem& p, const GetrfCtx& cx, int64_t k0, int64_t ns, int64_t c0, int64_t ncols, cudaStream_t s) {
   if (ns <= 0 || ncols <= 0) return 0;
   T* A = (T*)p.A + k0;   // rows relative to k0
+  if (ns <= DIRECT_NS) {
+    const unsigned grid = (unsigned)std::min<int64_t>(ncols, (int64_t)cx.sms * 8);
+    perm_apply_direct_kernel<T><<<grid, 256, 0, s>>>(p.dipiv, k0, (int)ns, (int)std::min<int64_t>(p.m - k0, INT_MAX), ncols, A + c0 * p.lda, p.lda);
+    count_launch();
+    return (int)cudaGetLastError();
+  }
   if (ns <= 256) {
     const unsigned grid = (unsigned)std::min<int64_t>(ncols, (int64_t)cx.sms * 8);
     perm_apply_fused_kernel<T><<<grid, 256, 0, s>>>((int)ns, ncols, cx.src_top, cx.disp_count, cx.disp_dst, cx.disp_src, A + c0 * p.lda, p.lda);
