@@ -964,6 +964,268 @@ getf2_reg_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __r
   cluster.sync();   // nobody exits while a peer may still access its shared memory
 }
 
+// ---- two chained 32-column phases in ONE launch (panel width NBP < nb <= 2 NBP, at least 2 NBP rows) ----------------------------
+// The lowest inner node of the panel recursion -- interchanges of the left leaf applied to the right one, a 32 x 32 row
+// solve, a rank-32 update, the right leaf, and the right leaf's interchanges applied back to the left one: five launches of
+// 7 - 40 us each on the critical path of ?getrf_ -- is folded into the leaf kernel: after phase 0 every thread GATHERS its
+// row of the next 32 columns from the position the interchanges so far assign to it (nothing has been written there yet),
+// every CTA forms U12 = L11^-1 A12 in shared memory (L11 read from CTA 0's column buffer through DSMEM, rotated forward
+// substitution by one warp), every thread subtracts L(r, 0:32) U12 from its row using ITS OWN multipliers, still in the column
+// buffer, phase 0 is flushed, and phase 1 runs the same column loop.  At the end CTA 0 applies phase 1's interchanges to the
+// L part of phase 0's columns (the same reverse-order bookkeeping as perm_apply_direct_kernel).
+template <typename T, int NBP, int RPT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+getf2_reg2_kernel(int64_t mrows, int nb, T* __restrict__ A, int64_t lda, int* __restrict__ ipiv, int64_t row_base,
+                  int* __restrict__ info, int64_t col_base) {
+  constexpr int NW = THREADS / 32, RT = RPT * THREADS;
+  static_assert(NW <= 32 && NBP <= 32 && THREADS >= 2 * NBP, "one lane per warp result / per panel column");
+  extern __shared__ __align__(16) unsigned char reg_smem[];
+  T* Lbuf = reinterpret_cast<T*>(reg_smem);   // Lbuf[c * RT + local row]: multipliers of column c of the CURRENT phase
+  __shared__ RegPanelTables<T, NBP> tab;
+  __shared__ T Ubuf[2 * NBP][NBP];            // CTA 0: Ubuf[K][j] = U(K, K + j) within K's phase
+  __shared__ T U12[NBP][NBP];                 // every CTA: rows 0 .. NBP-1 of the columns of phase 1
+  __shared__ T L11s[NBP][NBP + 1];            // every CTA: unit-lower block of phase 0
+  __shared__ int ipiv_s[2 * NBP];             // CTA 0: 1-based global rows
+  __shared__ int pivrel[2 * NBP];             // every CTA: pivot rows relative to the panel
+  __shared__ unsigned long long wbest[NW];
+  __shared__ int wrow[NW];
+  __shared__ T myrow[NBP], mykrow[NBP];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = (int)cluster.num_blocks(), cta = (int)cluster.block_rank(), tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int nb1 = nb - NBP;   // columns of phase 1
+  int rq[RPT];
+  T a[RPT][NBP];   // a[q][j] = current value of element (row rq[q], column K + j)
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    rq[q] = cta * RT + q * THREADS + tid;
+#pragma unroll
+    for (int c = 0; c < NBP; ++c) a[q][c] = rq[q] < mrows ? A[rq[q] + (int64_t)c * lda] : Sc<T>::zero();
+  }
+  cluster.sync();   // every CTA's shared memory is live before anybody writes into it remotely
+
+  // one phase: columns K0 .. K0 + nsteps - 1 of the panel (the column loop of getf2_reg_kernel with a row / column offset)
+  auto run_phase = [&](const int K0, const int nsteps) {
+#pragma unroll 1
+    for (int kk = 0; kk < nsteps; ++kk) {
+      const int K = K0 + kk, par = kk & 1;
+      unsigned long long best = 0ull;
+      int brow = INT_MAX;
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        if (rq[q] >= K && rq[q] < mrows) {
+          const unsigned long long sk = score_key(sc_score<T>(a[q][0]));
+          if (sk > best) { best = sk; brow = rq[q]; }
+        }
+      }
+      argmax_tree(best, brow);
+      if (lane == 0) { wbest[warp] = best; wrow[warp] = brow; }
+      __syncthreads();
+      unsigned long long cb = lane < NW ? wbest[lane] : 0ull;
+      int crow = lane < NW ? wrow[lane] : INT_MAX;
+      argmax_tree(cb, crow);
+      const int krow_cta = K / RT;
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        if (cb != 0ull && rq[q] == crow) {
+#pragma unroll
+          for (int c = 0; c < NBP; ++c) myrow[c] = a[q][c];
+        }
+        if (rq[q] == K) {
+#pragma unroll
+          for (int c = 0; c < NBP; ++c) mykrow[c] = a[q][c];
+        }
+      }
+      __syncthreads();
+      for (int idx = tid; idx < CL * NBP; idx += THREADS) {
+        const int peer = idx / NBP, c = idx % NBP;
+        RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, peer);
+        if (cb != 0ull) rt->vals[par][cta][c] = myrow[c];
+        if (cta == krow_cta) rt->rowk[par][c] = mykrow[c];
+      }
+      if (tid < CL) {
+        RegPanelTables<T, NBP>* rt = cluster.map_shared_rank(&tab, tid);
+        rt->score[par][cta] = cb;
+        rt->row[par][cta] = crow;
+      }
+      cluster.sync();
+      unsigned long long gb = 0ull;
+      int grow = INT_MAX;
+      if (lane < CL) {
+        gb = tab.score[par][lane];
+        if (gb != 0ull) grow = tab.row[par][lane];
+      }
+      const int my_row = grow;
+      argmax_tree(gb, grow);
+      const bool nonzero = gb > 1ull;
+      const int gw = __ffs(__ballot_sync(0xffffffffu, my_row == grow && grow != INT_MAX)) - 1;
+      const bool have = nonzero && gw >= 0;
+      const int piv = have ? grow : K;
+      const T* urow = have ? tab.vals[par][gw] : tab.rowk[par];
+      if (tid == 0) {
+        pivrel[K] = piv;
+        if (cta == 0) {
+          ipiv_s[K] = (int)(row_base + piv + 1);
+          if (!have) atomicMin(info, (int)(col_base + K + 1));
+        }
+      }
+      const bool helper = cta == 0 && warp == 1;
+      const bool swap_l = helper && piv != K && lane < kk;
+      T t1 = Sc<T>::zero(), t2 = Sc<T>::zero();
+      T* lk = nullptr;
+      T* lp = nullptr;
+      if (helper && lane < NBP) Ubuf[K][lane] = urow[lane];
+      if (swap_l) {
+        lk = cluster.map_shared_rank(Lbuf, K / RT) + (size_t)lane * RT + K % RT;
+        lp = cluster.map_shared_rank(Lbuf, piv / RT) + (size_t)lane * RT + piv % RT;
+        t1 = *lk; t2 = *lp;
+      }
+      const T inv_pv = have ? sc_fast_recip<T>(urow[0]) : Sc<T>::zero();
+#pragma unroll
+      for (int q = 0; q < RPT; ++q) {
+        if (piv != K && rq[q] == piv) {
+#pragma unroll
+          for (int c = 0; c < NBP; ++c) a[q][c] = tab.rowk[par][c];
+        }
+        const bool act = rq[q] > K && rq[q] < mrows;
+        T l = Sc<T>::zero();
+        if (act) {
+          l = have ? Sc<T>::mul(a[q][0], inv_pv) : a[q][0];
+          Lbuf[(size_t)kk * RT + q * THREADS + tid] = l;
+          if (!have) l = Sc<T>::zero();
+        }
+#pragma unroll
+        for (int j = 1; j < NBP; ++j) {
+          T v = a[q][j];
+          sc_fnma<T>(v, l, urow[j]);
+          a[q][j - 1] = v;
+        }
+        a[q][NBP - 1] = Sc<T>::zero();
+      }
+      if (swap_l) { *lk = t2; *lp = t1; }
+    }
+  };
+
+  run_phase(0, NBP);
+  cluster.sync();   // every multiplier and every interchange of phase 0 has landed in its column buffer
+
+  // ---- between the phases ------------------------------------------------------------------------------------------------
+  // source row of a panel position for the columns that have not been touched yet: undo the interchanges in reverse order
+  auto source_row = [&](int pos, int k_first, int k_last) {
+    for (int k = k_last; k >= k_first; --k) {
+      const int pk = pivrel[k];
+      if (pos == k) pos = pk; else if (pos == pk) pos = k;
+    }
+    return pos;
+  };
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    const int src = rq[q] < mrows ? source_row(rq[q], 0, NBP - 1) : 0;
+#pragma unroll
+    for (int c = 0; c < NBP; ++c) a[q][c] = (rq[q] < mrows && c < nb1) ? A[src + (int64_t)(NBP + c) * lda] : Sc<T>::zero();
+  }
+  // unit-lower L11 (CTA 0's column buffer, rows 0 .. NBP-1) and the gathered top block, into this CTA's shared memory
+  {
+    const T* L0 = cluster.map_shared_rank(Lbuf, 0);
+    for (int idx = tid; idx < NBP * NBP; idx += THREADS) {
+      const int i = idx % NBP, j = idx / NBP;
+      L11s[i][j] = i > j ? L0[(size_t)j * RT + i] : Sc<T>::zero();
+    }
+    for (int idx = tid; idx < NBP * NBP; idx += THREADS) {
+      const int i = idx % NBP, c = idx / NBP;
+      const int src = source_row(i, 0, NBP - 1);
+      U12[i][c] = c < nb1 ? A[src + (int64_t)(NBP + c) * lda] : Sc<T>::zero();
+    }
+  }
+  __syncthreads();
+  if (warp == 0 && lane < NBP) {   // U12 := L11^-1 U12, one column per lane, rotated forward substitution (unit diagonal)
+    T x[NBP];
+#pragma unroll
+    for (int i = 0; i < NBP; ++i) x[i] = U12[i][lane];
+#pragma unroll 1
+    for (int q = 0; q < NBP; ++q) {
+      const T xq = x[0];
+      U12[q][lane] = xq;
+#pragma unroll
+      for (int i = 1; i < NBP; ++i) {
+        T v = x[i];
+        if (q + i < NBP) sc_fnma<T>(v, L11s[q + i][q], xq);
+        x[i - 1] = v;
+      }
+    }
+  }
+  __syncthreads();
+  // rows below the first NBP: subtract L(r, 0:NBP) U12 using this thread's own multipliers; then flush phase 0
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (rq[q] >= NBP && rq[q] < mrows) {
+#pragma unroll 4
+      for (int k = 0; k < NBP; ++k) {
+        const T l = Lbuf[(size_t)k * RT + q * THREADS + tid];
+#pragma unroll
+        for (int c = 0; c < NBP; ++c) sc_fnma<T>(a[q][c], l, U12[k][c]);
+      }
+    }
+    if (rq[q] < mrows) {
+      const int ncol = min(rq[q], NBP);
+      for (int c = 0; c < ncol; ++c) A[rq[q] + (int64_t)c * lda] = Lbuf[(size_t)c * RT + q * THREADS + tid];
+    }
+  }
+  if (cta == 0) {
+    for (int idx = tid; idx < NBP * NBP; idx += THREADS) {
+      const int k = idx / NBP, j = idx % NBP;
+      if (k + j < NBP) A[k + (int64_t)(k + j) * lda] = Ubuf[k][j];                 // U of phase 0's own columns
+      if (j < nb1) A[k + (int64_t)(NBP + j) * lda] = U12[k][j];                      // rows 0 .. NBP-1 of phase 1's columns
+    }
+  }
+  cluster.sync();   // every remote read of phase 0's column buffers is done before phase 1 overwrites them
+
+  const int steps1 = nb1;   // mrows >= 2 NBP: every column of phase 1 has a pivot row
+  run_phase(NBP, steps1);
+  cluster.sync();
+#pragma unroll
+  for (int q = 0; q < RPT; ++q) {
+    if (rq[q] < mrows) {
+      const int ncol = max(0, min(rq[q] - NBP, steps1));   // columns NBP + c with NBP + c < r hold L(r, NBP + c)
+      for (int c = 0; c < ncol; ++c) A[rq[q] + (int64_t)(NBP + c) * lda] = Lbuf[(size_t)c * RT + q * THREADS + tid];
+    }
+  }
+  if (cta == 0) {
+    for (int idx = tid; idx < steps1 * NBP; idx += THREADS) {
+      const int k = idx / NBP, j = idx % NBP;
+      if (k + j < nb1) A[(NBP + k) + (int64_t)(NBP + k + j) * lda] = Ubuf[NBP + k][j];
+    }
+    if (tid < NBP + steps1) ipiv[tid] = ipiv_s[tid];
+  }
+  cluster.sync();   // every CTA's flush of phase 0 is visible: phase 1's interchanges on the L part of columns 0 .. NBP-1
+  if (cta == 0) {
+    // destinations: NBP + t (t < steps1) and the pivot rows outside that range; 2 * steps1 destinations x NBP columns
+    constexpr int PAIRS = (2 * NBP * NBP + THREADS - 1) / THREADS;
+    T v[PAIRS];
+    int dsts[PAIRS], cols[PAIRS];
+#pragma unroll
+    for (int e = 0; e < PAIRS; ++e) {
+      const int pidx = tid + e * THREADS;
+      const int d = pidx % (2 * NBP), c = pidx / (2 * NBP);
+      int dst = -1;
+      if (c < NBP) {
+        if (d < steps1) dst = NBP + d;
+        else if (d - NBP >= 0 && d - NBP < steps1 && pivrel[NBP + d - NBP] >= NBP + steps1) dst = pivrel[NBP + d - NBP];
+      }
+      int src = dst;
+      if (dst >= 0) src = source_row(dst, NBP, NBP + steps1 - 1);
+      dsts[e] = (dst >= 0 && src != dst) ? dst : -1;
+      cols[e] = c;
+      v[e] = dsts[e] >= 0 ? __ldcg(&A[src + (int64_t)c * lda]) : Sc<T>::zero();
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < PAIRS; ++e)
+      if (dsts[e] >= 0) A[dsts[e] + (int64_t)cols[e] * lda] = v[e];
+  }
+  cluster.sync();   // nobody exits while a peer may still access its shared memory
+}
+
 // ---- row interchanges as a permutation -----------------------------------------------------------------------------------
 // Simulate ipiv[k0 .. k0+ns) (1-based global rows, relative base row_base = k0) on an index array held in shared memory.
 // Output: src_top[k] = source row of destination row k (k < ns), and the list of displaced destinations r >= ns with
@@ -1173,18 +1435,24 @@ template <typename T>
 int reg_leaf_width(int64_t mrows) {
   static const int mode = [] { const char* e = getenv("B200BLAS_GETF2"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'c' ? 2 : 0)); }();
   if (mode != 0 || mrows > RegPanel<T>::ROWS_TALL) return Leaf<T>::NB;
-  return mrows <= RegPanel<T>::ROWS_WIDE ? RegPanel<T>::NBP_WIDE : RegPanel<T>::NBP_TALL;
+  const int w = mrows <= RegPanel<T>::ROWS_WIDE ? RegPanel<T>::NBP_WIDE : RegPanel<T>::NBP_TALL;
+  // two chained phases in one launch (getf2_reg2_kernel) double the leaf width; B200BLAS_GETF2_CHAIN=0 keeps single leaves
+  static const bool chain = [] { const char* e = getenv("B200BLAS_GETF2_CHAIN"); return !(e && e[0] == '0'); }();
+  return (chain && mrows >= 2 * w) ? 2 * w : w;
 }
 
 template <typename T, int NBP, int RPT>
 int launch_reg_panel(int64_t mrows, int nb, T* A, int64_t lda, int* ipiv, int64_t j0, int* info, cudaStream_t s) {
-  auto kern = getf2_reg_kernel<T, NBP, RPT, REG_THREADS>;
+  // up to NBP columns: one phase; up to 2 NBP (only offered when the panel has at least 2 NBP rows): two chained phases
+  auto kern = nb > NBP ? getf2_reg2_kernel<T, NBP, RPT, REG_THREADS> : getf2_reg_kernel<T, NBP, RPT, REG_THREADS>;
+  if (nb > NBP && (nb > 2 * NBP || mrows < 2 * NBP)) return (int)cudaErrorInvalidValue;
   {
     static std::atomic<uint64_t> done{0};
     int dev = 0;
     B200_CUDA_TRY(cudaGetDevice(&dev));
     if (!((done.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull)) {
-      B200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      B200_CUDA_TRY(cudaFuncSetAttribute(getf2_reg_kernel<T, NBP, RPT, REG_THREADS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      B200_CUDA_TRY(cudaFuncSetAttribute(getf2_reg2_kernel<T, NBP, RPT, REG_THREADS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
       done.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
     }
   }
@@ -1192,7 +1460,8 @@ int launch_reg_panel(int64_t mrows, int nb, T* A, int64_t lda, int* ipiv, int64_
   if (cl < 1) cl = 1;
   cudaLaunchConfig_t cfg = {};
   constexpr size_t lbuf_bytes = (size_t)NBP * RPT * REG_THREADS * sizeof(T);   // 128 KB in every configuration
-  B200_SET_MAX_DYN_SMEM_ONCE(kern, lbuf_bytes);
+  B200_SET_MAX_DYN_SMEM_ONCE((getf2_reg_kernel<T, NBP, RPT, REG_THREADS>), lbuf_bytes);
+  B200_SET_MAX_DYN_SMEM_ONCE((getf2_reg2_kernel<T, NBP, RPT, REG_THREADS>), lbuf_bytes);
   cfg.gridDim = dim3(cl); cfg.blockDim = dim3(REG_THREADS); cfg.dynamicSmemBytes = lbuf_bytes; cfg.stream = s;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
