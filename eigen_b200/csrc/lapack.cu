@@ -1436,8 +1436,12 @@ int reg_leaf_width(int64_t mrows) {
   static const int mode = [] { const char* e = getenv("B200BLAS_GETF2"); return !e ? 0 : (e[0] == 's' ? 1 : (e[0] == 'c' ? 2 : 0)); }();
   if (mode != 0 || mrows > RegPanel<T>::ROWS_TALL) return Leaf<T>::NB;
   const int w = mrows <= RegPanel<T>::ROWS_WIDE ? RegPanel<T>::NBP_WIDE : RegPanel<T>::NBP_TALL;
-  // two chained phases in one launch (getf2_reg2_kernel) double the leaf width; B200BLAS_GETF2_CHAIN=0 keeps single leaves
-  static const bool chain = [] { const char* e = getenv("B200BLAS_GETF2_CHAIN"); return !(e && e[0] == '0'); }();
+  // two chained phases in one launch (getf2_reg2_kernel) double the leaf width.  Measured on B200 (profiles/bench_r02/
+  // level3_pass11_chained_leaf.txt): sgetrf 8192 35.9 -> 32.2 ms, dgetrf 8192 36.2 -> 36.8 ms (the 8-byte types run the chained
+  // kernel at 128 registers with spills in the column loop, 181 us against 2 x 64 us + the folded launches), so the default
+  // is on for float only; B200BLAS_GETF2_CHAIN=1 / 0 forces it on / off for every type.
+  static const int chain_env = [] { const char* e = getenv("B200BLAS_GETF2_CHAIN"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
+  const bool chain = chain_env >= 0 ? chain_env == 1 : sizeof(T) == 4;
   return (chain && mrows >= 2 * w) ? 2 * w : w;
 }
 
