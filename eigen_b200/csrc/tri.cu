@@ -549,12 +549,16 @@ int run_tri(const TriProblem& p, cudaStream_t s) {
     const bool t_lower = (p.uplo == UPLO_LOWER) == (p.op == OP_N);
     // leaves: B200BLAS_TRSM=inv forces the inverse-based leaves (one batched inversion of all diagonal blocks, then every
     // leaf is a product on the tensor-pipe kernels), =subst the substitution leaf; default: inverse leaves for large solves
-    // (measured on B200, profiles/bench_r02: dtrsm 8192 21.9 -> 28.3 TFLOP/s), substitution where the inversion of the
+    // (measured on B200, profiles/bench_r02: dtrsm 8192 21.9 -> 28.3 TFLOP/s at best), substitution where the inversion of the
     // whole triangle would not be amortised (the panel solves inside ?potrf_ / ?getrf_)
     static const int leaf_env = [] { const char* e = getenv("B200BLAS_TRSM"); return !e ? 0 : (e[0] == 'i' ? 1 : (e[0] == 's' ? 2 : 0)); }();
     constexpr int LB = LeafOrder<T>::NB * LeafOrder<T>::NSUB;
     const int64_t na = p.left ? p.m : p.n, nrhs = p.left ? p.n : p.m;
-    const bool use_inv = leaf_env == 1 || (leaf_env == 0 && na >= 2048 && nrhs >= 1024);
+    // (final pass of round 2: with the shared-memory block solve as the leaf, a lower canonical solve runs at 26.6 TFLOP/s
+    // without any workspace, run to run; the inverse path measured 19 - 28 TFLOP/s depending on the stream-ordered
+    // allocator, so it is kept for the UPPER canonical solves only, whose leaf is still the one-vector-per-thread kernel)
+    const bool s_lower_all = p.left ? t_lower : !t_lower;
+    const bool use_inv = leaf_env == 1 || (leaf_env == 0 && !s_lower_all && na >= 2048 && nrhs >= 1024);
     if (SOLVE && p.Vinv && p.Xtmp) {   // the caller (lapack.cu) already holds the inverses of the diagonal blocks
       B200_CUDA_TRY((tri_recurse<T, SOLVE>(p, t_lower, 0, na, s)));
     } else if (SOLVE && use_inv) {
