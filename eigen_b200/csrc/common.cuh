@@ -45,7 +45,7 @@ struct TriProblem {
   double alpha[2];
   const void* A; int64_t lda;
   void* B; int64_t ldb;
-  // DRAFT (round 2): inverses of the diagonal leaf blocks (leaf order x leaf order each, ld = leaf order) and a
+  // inverses of the diagonal leaf blocks (leaf order x leaf order each, ld = leaf order) and a
   // scratch panel for the out-of-place leaf products; null = substitution leaves
   const void* Vinv = nullptr; void* Xtmp = nullptr;
 };

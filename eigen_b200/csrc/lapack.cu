@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32) potf2_leaf_kernel(int upper, int d, int64_
     }
 }
 
-// ---- DRAFT (round 2, not yet run on hardware; opt-in with B200BLAS_POTF2=cta) --------------------------------------------
+// ---- forced variant of the recursive path (B200BLAS_POTRF=rec B200BLAS_POTF2=cta; 115 tests green on B200, pass 1b) -----------
 // CTA-wide Cholesky leaf of order d <= NBL: the block lives in shared memory, every column costs two __syncthreads and
 // its trailing update is spread over all 256 threads (the one-warp leaf issues ~8k dependent instructions per 32 x 32
 // block = 34 us; profiles/launches_r01_dpotrf8192_v2.md).
@@ -453,7 +453,7 @@ int potrf_rec(const PotrfProblem& p, int64_t d0, int64_t d, cudaStream_t s) {
   const bool upper = p.uplo == UPLO_UPPER;
   const bool cplx = sizeof(T) != sizeof(typename Sc<T>::real);
   T* A = (T*)p.A;
-  static const bool cta_leaf = [] { const char* e = getenv("B200BLAS_POTF2"); return e && e[0] == 'c'; }();   // DRAFT, opt-in
+  static const bool cta_leaf = [] { const char* e = getenv("B200BLAS_POTF2"); return e && e[0] == 'c'; }();   // forced variant, opt-in
   constexpr int NBL = 64 / (sizeof(T) == 16 ? 2 : 1);   // 64 x 65 elements of <= 8 bytes, 32 x 33 of 16 bytes
   if (cta_leaf && d <= NBL) {
     potf2_cta_kernel<T, NBL><<<1, 256, 0, s>>>(upper ? 1 : 0, (int)d, d0, A + d0 + d0 * p.lda, p.lda, p.dinfo);
@@ -636,7 +636,8 @@ getf2_panel_kernel(int64_t mrows, int nb, int rows_per_cta, T* __restrict__ A, i
     for (int r = tid; r < R; r += 256) A[(r0 + r) + (int64_t)c * lda] = slab[r * LDS + c];
 }
 
-// ---- DRAFT (round 2, compiled but not yet run on hardware; opt-in with B200BLAS_GETF2=cluster) ---------------------------
+// ---- forced variant (B200BLAS_GETF2=cluster; 115 tests green on B200, pass 1b; no faster than the cooperative grid: the slab
+// arithmetic, not the barrier, was the bound -- which is what led to the register-resident panel below) ---------------------------
 // The same panel factorization on ONE thread-block cluster: the slab of every CTA lives in its shared memory, the
 // per-column exchange goes through distributed shared memory and the barrier is the hardware cluster barrier instead
 // of a global-atomic grid barrier (4.1 us per column in round 1, profiles/launches_r01_dgetrf8192_v2.md).

@@ -296,7 +296,7 @@ tri_block_solve_kernel(int left, int op, int uplo, int unit, int nb, int64_t nrh
   }
 }
 
-// ---- DRAFT (round 2, compiled but not yet run on hardware; opt-in with B200BLAS_TRSM=inv) --------------------------------
+// ---- inverse-based leaves (default for large UPPER canonical solves, B200BLAS_TRSM=inv forces them everywhere) --------------------
 // Inverses of all diagonal leaf blocks of T = op(A) in ONE launch (one CTA per block), so that a leaf of the solve is a
 // product X_b = inv(T_bb) * B_b on the tensor-pipe kernels instead of 8256 FMA + LDS per right-hand side on the SIMT
 // pipe (profiles/launches_r01_dpotrf8192_v2.md).  The block is brought to lower-canonical form Lc (T itself, or T^T
@@ -439,7 +439,7 @@ int launch_leaf(const TriProblem& p, bool s_lower, int64_t d0, int nb, cudaStrea
   const T* A = (const T*)p.A + d0 + d0 * p.lda;
   T* B = p.left ? (T*)p.B + d0 : (T*)p.B + d0 * p.ldb;
   const int64_t nrhs = p.left ? p.n : p.m;
-  if (SOLVE && p.Vinv) {   // DRAFT: X_b = inv(T_bb) * B_b (or B_b * inv(T_bb)) out of place, then copied back
+  if (SOLVE && p.Vinv) {   // X_b = inv(T_bb) * B_b (or B_b * inv(T_bb)) out of place on the tensor pipe, then copied back
     const T* Vb = (const T*)p.Vinv + (d0 / LB) * (int64_t)LB * LB;
     GemmProblem g;
     g.type = p.type; g.opa = OP_N; g.opb = OP_N; g.k = nb;
