@@ -8,6 +8,8 @@
 // Host operands are staged through CUDA streams: A is uploaded once, B and C travel in column slabs so that the
 // upload of slab j+1, the product on slab j and the download of slab j-1 overlap (the GPU analogue of the kc/nc
 // panel streaming of GeneralMatrixMatrix.h:155-198).  There is no CPU fallback.
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
 #include <chrono>
 #include <climits>
@@ -49,6 +51,19 @@ static bool log_enabled() {
   static const bool v = [] { const char* e = getenv("B200BLAS_LOG"); return e && e[0] && e[0] != '0'; }();
   return v;
 }
+// B200BLAS_NVTX=1: one NVTX range per entry point (header-only nvtx3: no link dependency, a no-op unless a tool such as
+// Nsight Systems is attached) -- SURVEY section 5, tracing.
+static bool nvtx_enabled() {
+  static const bool v = [] { const char* e = getenv("B200BLAS_NVTX"); return e && e[0] && e[0] != '0'; }();
+  return v;
+}
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_enabled()) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 static double wall_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -330,6 +345,7 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
 static int gemm_entry(int type, const char* ta, const char* tb, const int* pm, const int* pn, const int* pk,
                       const void* palpha, const void* a, const int* plda, const void* b, const int* pldb,
                       const void* pbeta, void* c, const int* pldc) {
+  NvtxRange nvtx_range("b200blas ?gemm_");
   const int opa = op_of(*ta), opb = op_of(*tb);
   int info = check_args(opa, opb, *pm, *pn, *pk, *plda, *pldb, *pldc);
   if (info) return xerbla_(k_names[type], &info, 6);
@@ -419,6 +435,7 @@ static int run_host_rankk(const GemmProblem& hp) {
 
 static int rankk_entry(int type, bool herk, const char* uplo, const char* op, const int* pn, const int* pk, const void* palpha,
                        const void* a, const int* plda, const void* pbeta, void* c, const int* pldc) {
+  NvtxRange nvtx_range("b200blas ?syrk_/?herk_");
   const bool cplx = (type == TY_C || type == TY_Z);
   const char* name = herk ? k_herk_names[type] : k_syrk_names[type];
   const int ul = (*uplo == 'U' || *uplo == 'u') ? UPLO_UPPER : (*uplo == 'L' || *uplo == 'l') ? UPLO_LOWER : -1;
@@ -525,6 +542,7 @@ static const char* k_trmm_names[4] = {"STRMM ", "DTRMM ", "CTRMM ", "ZTRMM "};
 // blas/level3_impl.h:78-178 (trsm) and :183-284 (trmm)
 static int tri_entry(int type, bool solve, const char* side, const char* uplo, const char* opa, const char* diag, const int* pm,
                      const int* pn, const void* palpha, const void* a, const int* plda, void* b, const int* pldb) {
+  NvtxRange nvtx_range("b200blas ?trsm_/?trmm_");
   const char* name = solve ? k_trsm_names[type] : k_trmm_names[type];
   const int sd = side_of(*side), ul = uplo_of(*uplo), o = op_of(*opa), dg = diag_of(*diag);
   int info = 0;
@@ -587,6 +605,7 @@ static const char* k_hemm_names[4] = {"", "", "CHEMM ", "ZHEMM "};
 // blas/level3_impl.h:287-355 (symm) and :505-562 (hemm)
 static int symm_entry(int type, bool herm, const char* side, const char* uplo, const int* pm, const int* pn, const void* palpha,
                       const void* a, const int* plda, const void* b, const int* pldb, const void* pbeta, void* c, const int* pldc) {
+  NvtxRange nvtx_range("b200blas ?symm_/?hemm_");
   const char* name = herm ? k_hemm_names[type] : k_symm_names[type];
   const int sd = side_of(*side), ul = uplo_of(*uplo);
   int info = 0;
@@ -659,6 +678,7 @@ static const char* k_her2k_names[4] = {"", "", "CHER2K", "ZHER2K"};
 //   C.tri = alpha * op(A) op(B)^T|^H + beta * C.tri,   then   C.tri += alpha|conj(alpha) * op(B) op(A)^T|^H
 static int r2k_entry(int type, bool her, const char* uplo, const char* op, const int* pn, const int* pk, const void* palpha,
                      const void* a, const int* plda, const void* b, const int* pldb, const void* pbeta, void* c, const int* pldc) {
+  NvtxRange nvtx_range("b200blas ?syr2k_/?her2k_");
   const bool cplx = (type == TY_C || type == TY_Z);
   const char* name = her ? k_her2k_names[type] : k_syr2k_names[type];
   const int ul = uplo_of(*uplo), o = op_of(*op);
@@ -744,6 +764,7 @@ struct DevInts {
 };
 
 static int potrf_entry(int type, const char* uplo, const int* pn, void* a, const int* plda, int* info) {
+  NvtxRange nvtx_range("b200blas ?potrf_");
   const int ul = uplo_of(*uplo);
   *info = 0;
   if (ul < 0) *info = -1;
@@ -786,6 +807,7 @@ static int potrf_entry(int type, const char* uplo, const int* pn, void* a, const
 }
 
 static int getrf_entry(int type, const int* pm, const int* pn, void* a, const int* plda, int* ipiv, int* info) {
+  NvtxRange nvtx_range("b200blas ?getrf_");
   *info = 0;
   if (*pm < 0) *info = -1;
   else if (*pn < 0) *info = -2;
@@ -903,6 +925,7 @@ int zherk_(const char* uplo, const char* trans, const int* n, const int* k, cons
 int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, const void* alpha, const void* dA,
                       int64_t lda, const void* dB, int64_t ldb, const void* beta, void* dC, int64_t ldc, void* stream,
                       int variant) {
+  NvtxRange nvtx_range("b200blas_gemm_dev");
   if (type < 0 || type > 3) return -1;
   const int opa = op_of(transa), opb = op_of(transb);
   int info = check_args(opa, opb, m, n, k, lda, ldb, ldc);
@@ -926,6 +949,7 @@ int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, c
 // entry runs the product on the sm_100a kernels instead; otherwise it returns 1 and the caller keeps its own path.
 int b200blas_contract_dev(int type, int64_t m, int64_t n, int64_t k, const void* lhs, int64_t lhs_row_stride, int64_t lhs_col_stride,
                           const void* rhs, int64_t rhs_row_stride, int64_t rhs_col_stride, void* out, int64_t ldo, void* stream) {
+  NvtxRange nvtx_range("b200blas_contract_dev");
   if (type < 0 || type > 3 || m < 0 || n < 0 || k < 0 || !out) return -1;
   if (m == 0 || n == 0) return 0;
   if (m > INT_MAX || n > INT_MAX || k > INT_MAX || !lhs || !rhs) return 1;

@@ -160,6 +160,10 @@ int b200blas_gemm_dev(int type, char transa, char transb, int m, int n, int k, c
 int b200blas_contract_dev(int type, int64_t m, int64_t n, int64_t k, const void* lhs, int64_t lhs_row_stride, int64_t lhs_col_stride,
                           const void* rhs, int64_t rhs_row_stride, int64_t rhs_col_stride, void* out, int64_t ldo, void* stream);
 
+/* Tracing: B200BLAS_LOG=1 prints one line per product call on stderr (shape, operand residency, devices,
+ * kernel variant, wall ms, bytes moved); B200BLAS_NVTX=1 opens one NVTX range per entry point (header-only nvtx3: nothing is
+ * linked, nothing happens unless a profiler is attached). */
+
 /* introspection used by tests and bench.py */
 int b200blas_version(void);
 int b200blas_device_ok(void);                 /* 1 if the current device is sm_100 and the kernels loaded */
