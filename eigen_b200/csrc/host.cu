@@ -205,7 +205,8 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
   // column slabs of C (and of op(B)): ~16 slabs, at least 512 columns wide, multiples of 256 columns
   const double total_bytes = (double)es * ((double)m * k + (double)k * n + 2.0 * m * n);
   int64_t slab = n;
-  if (total_bytes > 32e6 && n >= 1024) slab = std::max<int64_t>(512, round_up((n + 15) / 16, 256));
+  static const int slabs_env = [] { const char* e = getenv("B200BLAS_HOST_SLABS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+  if (total_bytes > 32e6 && n >= 1024) slab = std::max<int64_t>(512, round_up((n + slabs_env - 1) / slabs_env, 256));
   int nslabs = (int)((n + slab - 1) / slab);
   if (nslabs > Staging::MAX_SLABS) { slab = round_up((n + Staging::MAX_SLABS - 1) / Staging::MAX_SLABS, 256); nslabs = (int)((n + slab - 1) / slab); }
 
@@ -221,8 +222,10 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
     std::thread& t; std::mutex& mu; std::condition_variable& cv; bool& abort;
     ~JoinGuard() { if (t.joinable()) { { std::lock_guard<std::mutex> l(mu); abort = true; } cv.notify_all(); t.join(); } }
   } join_guard{downloader, dl_mu, dl_cv, dl_abort};
+  // B200BLAS_HOST_HEAD=simple: round 2's first schedule (8 chunks of A, head slabs complete their inputs before A1 travels)
+  static const bool staircase = [] { const char* e = getenv("B200BLAS_HOST_HEAD"); return !(e && e[0] == 's'); }();
   int nac = 1;
-  if (have_product && nslabs > 1 && k >= 8 * 512) nac = Staging::MAX_ACHUNKS;
+  if (have_product && nslabs > 1 && k >= 8 * 512) nac = staircase ? Staging::MAX_ACHUNKS : 8;
   const int64_t kch = round_up((k + nac - 1) / nac, 256);
   auto upload_a_chunk = [&](int c) -> int {
     const int64_t k0 = (int64_t)c * kch, kc = std::min<int64_t>(kch, k - k0);
@@ -309,6 +312,43 @@ static int run_host(int type, int opa, int opb, int64_t m, int64_t n, int64_t k,
   // worth.  Uploads are issued in order of first use: B0 C0 A0 | B1 C1 | B2 C2 | B3 C3 | A1 | A2 ...  Later slabs see A resident
   // and run at full k.
   const int head = !have_product ? 0 : (nac > 1 ? std::min(nslabs, 4) : std::min(nslabs, 1));
+  if (staircase && head > 1) {
+    // Staircase: uploads alternate between chunks of A and the inputs of the head slabs -- S0 A0 | A1 S1 | A2 S2 | A3 S3 | A4 A5 ...
+    // (S_h = B_h and C_h) -- and every arrival releases the products it completes the inputs of: chunk c against every slab
+    // that has arrived, slab h against every chunk that has arrived.  The first product starts after one slab and one
+    // (half-size) chunk instead of after four slabs and one chunk, and the arithmetic released per arrival grows with the bytes
+    // still to come; the products accumulate into their slab in whatever order they are released (beta on the first one).
+    const int nch = (int)((k + kch - 1) / kch);
+    std::vector<int> done(head, 0);
+    int a_arrived = 0, s_arrived = 0;
+    auto product = [&](int cix, int h) -> int {
+      const int64_t k0 = (int64_t)cix * kch, kc = std::min<int64_t>(kch, k - k0);
+      GemmProblem q = slab_problem(h);
+      q.k = kc;
+      q.A = (opa == OP_N) ? dA + (size_t)k0 * dlda * es : dA + (size_t)k0 * es;
+      q.B = (opb == OP_N) ? (const char*)q.B + (size_t)k0 * es : (const char*)q.B + (size_t)k0 * dldb * es;
+      if (done[h] > 0) { q.beta[0] = 1.0; q.beta[1] = 0.0; }
+      { const int e = run_device(q, st.s_comp, B200BLAS_AUTO); if (e) { cudaDeviceSynchronize(); return e; } }
+      if (++done[h] == nch) return return_slab(h);
+      return 0;
+    };
+    auto arrive_slab = [&]() -> int {
+      const int h = s_arrived;
+      { const int e = upload_slab_inputs(h); if (e) return e; }   // also makes s_comp wait for it
+      ++s_arrived;
+      for (int cix = 0; cix < a_arrived; ++cix) { const int e = product(cix, h); if (e) return e; }
+      return 0;
+    };
+    { const int e = arrive_slab(); if (e) return e; }
+    for (int cix = 0; cix < nch; ++cix) {
+      { const int e = upload_a_chunk(cix); if (e) return e; }
+      B200_CUDA_TRY(cudaStreamWaitEvent(st.s_comp, st.ev_ac[cix], 0));
+      ++a_arrived;
+      for (int h = 0; h < s_arrived; ++h) { const int e = product(cix, h); if (e) return e; }
+      if (cix >= 1 && s_arrived < head) { const int e = arrive_slab(); if (e) return e; }
+    }
+    while (s_arrived < head) { const int e = arrive_slab(); if (e) return e; }
+  } else
   for (int cix = 0; cix < nac && head > 0; ++cix) {
     const int64_t k0 = (int64_t)cix * kch, kc = std::min<int64_t>(kch, k - k0);
     if (kc <= 0) break;

@@ -258,7 +258,7 @@ struct Staging {
   void* dbuf[3] = {nullptr, nullptr, nullptr};
   size_t dcap[3] = {0, 0, 0};
   static constexpr int MAX_SLABS = 64;
-  static constexpr int MAX_ACHUNKS = 8;
+  static constexpr int MAX_ACHUNKS = 16;
   cudaEvent_t ev_in[MAX_SLABS] = {}, ev_comp[MAX_SLABS] = {}, ev_ac[MAX_ACHUNKS] = {}, ev_a = nullptr;
   bool ready = false;
   PinnedRing ring_in, ring_out;   // pageable operands only
