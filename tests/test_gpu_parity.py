@@ -397,3 +397,21 @@ def test_tf32x3_huge_and_infinite_inputs(L, t):
             assert not np.isfinite(x[bad]).any() and not np.isfinite(s[bad]).any()
             assert np.isfinite(x[~bad]).all()
             assert np.abs(x[~bad] - s[~bad]).max() <= 64 * oa.EPS[t] * np.abs(s[~bad]).max()
+
+
+@pytest.mark.parametrize("head", ["staircase", "simple"])
+def test_host_pipeline_head_with_chunked_a(L, head):
+    """Host-operand products large enough for the multi-slab / chunked-A head of host.cu::run_host (k >= 4096, n >= 1024): the
+    first slabs accumulate chunk by chunk while A is still on the bus, in whatever order the arrivals release the products
+    (default: the staircase; B200BLAS_HOST_HEAD=simple: the four-slab head of the first schedule) -- N/T/C operands,
+    alpha / beta != 1, beta = 0 with NaN in C, ld = dim + 1, ragged last chunk.  Same cases as tools/host_head_check.py, in a
+    fresh process because the schedule is read once per process."""
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.pop("B200BLAS_HOST_HEAD", None)
+    if head == "simple":
+        env["B200BLAS_HOST_HEAD"] = "simple"
+    p = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "host_head_check.py")], env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, timeout=600, text=True)
+    assert p.returncode == 0 and "all cases passed" in p.stdout, p.stdout[-3000:]
